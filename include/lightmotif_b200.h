@@ -1,0 +1,255 @@
+/*
+ * lightmotif_b200.h -- C ABI of the B200-native PWM scanning engine.
+ *
+ * This is the drop-in boundary for the `lightmotif::pli` pipeline traits of
+ * althonos/lightmotif (reference @ 9df9a159, v0.10.1).  Every entry point
+ * cites the reference interface it replaces (paths relative to the lightmotif
+ * repository).  A Rust back-end (`struct Cuda; impl Backend for Cuda`) binds
+ * these symbols one-to-one -- see INTEGRATION.md and bindings/rust/.
+ *
+ * Conventions
+ *  - every function returns an `int` status: LM_OK (0), LM_EMPTY (1, the
+ *    reference's `None`), or a negative LM_ERR_* code; nothing unwinds across
+ *    the ABI (the reference panics, e.g. avx2.rs:832-837; the Rust shim turns
+ *    LM_ERR_WRAP back into that panic);
+ *  - buffers are plain pointers + sizes; host pointers are borrowed for the
+ *    duration of the call only; device memory is owned by `lm_ctx` / `lm_seq`
+ *    handles with explicit free;
+ *  - the striped layout is the reference's: `[rows + wrap][32]` u8, row
+ *    stride 32 bytes (DenseMatrix<Symbol, U32>, dense.rs:43-55,125-128),
+ *    cell (r, c) = symbol at sequence index c * rows + r, default symbol
+ *    (N / X) past the end (pli/mod.rs:178-200, seq.rs:369-381);
+ *  - score matrices are `[rows][32]` f32 / u8 with a caller-given row stride
+ *    in ELEMENTS (DenseMatrix<f32, U32>::stride() == 32);
+ *  - a PSSM is `[m][pssm_stride]` with K valid columns per row (K = 5 DNA,
+ *    21 protein; DenseMatrix<f32, K> stride is 8 / 24 floats, <u8, K> is 32).
+ *    Columns >= K are never read (they are uninitialised padding in Rust);
+ *  - an `lm_ctx` is NOT thread-safe: use one per host thread (the reference's
+ *    `Pipeline` is stateless and Clone, pli/mod.rs:227-231).  Different
+ *    contexts may be used concurrently, also on the same device.
+ */
+#ifndef LIGHTMOTIF_B200_H
+#define LIGHTMOTIF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_ABI_VERSION 1
+#define LM_LANES 32 /* <Avx2 as Backend>::Lanes = U32, avx2.rs:33-35 */
+
+/* status codes */
+#define LM_OK 0
+#define LM_EMPTY 1               /* Option::None (empty scores) */
+#define LM_ERR_INVALID_ARG (-1)
+#define LM_ERR_INVALID_SYMBOL (-2) /* err.rs:10 InvalidSymbol; *bad_index is set */
+#define LM_ERR_WRAP (-3)           /* avx2.rs:832-837 "not enough wrapping rows" */
+#define LM_ERR_CUDA (-4)
+#define LM_ERR_OOM (-5)
+#define LM_ERR_UNSUPPORTED (-6)    /* err.rs:34 UnsupportedBackend / size limits */
+#define LM_ERR_OVERFLOW (-7)       /* hit buffer too small; *count holds the total */
+
+/* alphabets (abc.rs:88-110 Dna "ACTGN", abc.rs:190-228 Protein "ACDEFGHIKLMNPQRSTVWYX") */
+#define LM_DNA 0
+#define LM_PROTEIN 1
+
+/* argmax tie rules: which reference back-end to reproduce */
+#define LM_RULE_GENERIC 0 /* pli/mod.rs:135-155: last row, then last column */
+#define LM_RULE_AVX2 1    /* avx2.rs:349-426: first column, last row in it; (0,0) quirk */
+#define LM_RULE_SSE2 2    /* sse2.rs:175-261: last column, last row in it */
+
+typedef struct lm_ctx lm_ctx;
+typedef struct lm_seq lm_seq;
+
+/* MatrixCoordinates (dense.rs:28-39) plus the score of the cell.
+ * `position` = col * rows + row = StripedScores::offset (scores.rs:155-157),
+ * computed with the number of score rows of the call. */
+typedef struct lm_hit {
+  uint64_t row;
+  uint64_t position;
+  uint32_t col;
+  float score; /* for u8 calls: the u8 score converted to float */
+} lm_hit;
+
+/* per-column winner: the highest score of a column and the LAST row that
+ * attains it (what avx2.rs:373-403 keeps in s1..s4 / p1..p4).  `valid` is 0
+ * for an empty row range. */
+typedef struct lm_colwin {
+  uint64_t row;
+  float score;
+  uint32_t valid;
+} lm_colwin;
+
+/* ------------------------------------------------------------- lifecycle */
+
+int lm_abi_version(void);
+const char *lm_strerror(int status);
+/* message of the last failing CUDA call on this context ("" if none) */
+const char *lm_ctx_last_error(const lm_ctx *ctx);
+
+/* Pipeline::<A, Cuda>::cuda() -> Result<Self, UnsupportedBackend>
+ * (mirrors pli/mod.rs:401-407 Pipeline::avx2()).  LM_ERR_UNSUPPORTED when no
+ * sm_100 device is present. */
+int lm_ctx_create(int device, lm_ctx **out);
+/* Same, but enqueue all work on an existing CUDA stream (cudaStream_t) so the
+ * caller can bracket calls with its own events. */
+int lm_ctx_create_on_stream(int device, void *cuda_stream, lm_ctx **out);
+void lm_ctx_destroy(lm_ctx *ctx);
+void *lm_ctx_stream(lm_ctx *ctx);
+int lm_ctx_synchronize(lm_ctx *ctx);
+/* number of kernels this library launched through `ctx` so far */
+uint64_t lm_ctx_kernel_launches(const lm_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) spent in the kernels
+ * of the most recent scoring call */
+float lm_ctx_last_kernel_ms(const lm_ctx *ctx);
+
+/* --------------------------------------------- host-buffer trait mirrors */
+
+/* Encode::encode_into (pli/mod.rs:56-66; avx2.rs:37-99).  On an invalid byte
+ * returns LM_ERR_INVALID_SYMBOL with *bad_index = index of the FIRST invalid
+ * byte (the Rust shim rebuilds InvalidSymbol(seq[bad_index] as char)). */
+int lm_encode(lm_ctx *ctx, int alphabet, const uint8_t *ascii, size_t n,
+              uint8_t *dst, size_t *bad_index);
+/* EncodedSequence::encode_lossy (seq.rs:122-129): unknown -> default symbol */
+int lm_encode_lossy(lm_ctx *ctx, int alphabet, const uint8_t *ascii, size_t n,
+                    uint8_t *dst);
+/* Stripe::stripe_into (pli/mod.rs:178-200; avx2.rs:561-799).  dst is
+ * [ceil(n/32)][dst_stride] bytes; cells past n get the default symbol. */
+int lm_stripe(lm_ctx *ctx, int alphabet, const uint8_t *sym, size_t n,
+              uint8_t *dst, size_t dst_stride);
+/* StripedSequence::configure_wrap (seq.rs:369-381): fills rows
+ * [rows, rows + wrap) of `data` ([rows + wrap][stride]). */
+int lm_configure_wrap(lm_ctx *ctx, int alphabet, uint8_t *data, size_t rows,
+                      size_t stride, size_t wrap);
+
+/* Score<f32, A, U32>::score_rows_into (pli/mod.rs:72-106; avx2.rs:817-904).
+ * seq is the host striped matrix [rows + wrap][seq_stride]; `length` is
+ * StripedSequence::len().  Writes *out_rows = 0 and returns LM_OK when
+ * length < m or the range is empty (the reference's resize(0, 0)); otherwise
+ * fills out[0 .. row_end-row_begin][32] and *out_rows = row_end - row_begin.
+ * LM_ERR_WRAP if wrap < m - 1. */
+int lm_score_f32_rows(lm_ctx *ctx, int alphabet, const float *pssm, size_t m,
+                      size_t pssm_stride, const uint8_t *seq, size_t rows,
+                      size_t wrap, size_t seq_stride, size_t length,
+                      size_t row_begin, size_t row_end, float *out,
+                      size_t out_stride, size_t *out_rows);
+/* Score<u8, Dna, U32>::score_rows_into (avx2.rs:292-347, 907-941): saturating
+ * u8 sums (_mm256_adds_epu8). */
+int lm_score_u8_rows(lm_ctx *ctx, int alphabet, const uint8_t *dm, size_t m,
+                     size_t dm_stride, const uint8_t *seq, size_t rows,
+                     size_t wrap, size_t seq_stride, size_t length,
+                     size_t row_begin, size_t row_end, uint8_t *out,
+                     size_t out_stride, size_t *out_rows);
+
+/* Maximum::argmax / max (pli/mod.rs:135-160; avx2.rs:349-467) over a host
+ * score matrix [rows][stride].  LM_EMPTY when rows == 0.  lm_max_* return the
+ * true maximum (the generic definition); the AVX2 `max` quirk (accumulators
+ * start at 0.0, avx2.rs:438-441) is NOT reproduced. */
+int lm_argmax_f32(lm_ctx *ctx, const float *scores, size_t rows, size_t stride,
+                  int rule, lm_hit *best);
+int lm_max_f32(lm_ctx *ctx, const float *scores, size_t rows, size_t stride,
+               float *best);
+int lm_argmax_u8(lm_ctx *ctx, const uint8_t *scores, size_t rows, size_t stride,
+                 int rule, lm_hit *best);
+int lm_max_u8(lm_ctx *ctx, const uint8_t *scores, size_t rows, size_t stride,
+              uint8_t *best);
+/* Threshold::threshold (pli/mod.rs:210-221): every cell >= t, returned in the
+ * reference's row-major order.  *count is always the total number of hits;
+ * LM_ERR_OVERFLOW if it exceeds cap (the first `cap` hits are still written). */
+int lm_threshold_f32(lm_ctx *ctx, const float *scores, size_t rows,
+                     size_t stride, float t, lm_hit *hits, size_t cap,
+                     size_t *count);
+int lm_threshold_u8(lm_ctx *ctx, const uint8_t *scores, size_t rows,
+                    size_t stride, uint8_t t, lm_hit *hits, size_t cap,
+                    size_t *count);
+
+/* ------------------------------------------- device-resident sequences */
+
+/* EncodedSequence::encode / encode_lossy -> to_striped -> configure_wrap in
+ * ONE device pass from raw ASCII (seq.rs:111-129,168-175,369-381).
+ * lossy == 0: LM_ERR_INVALID_SYMBOL + *bad_index as lm_encode. */
+int lm_seq_from_ascii(lm_ctx *ctx, int alphabet, const uint8_t *ascii, size_t n,
+                      int lossy, size_t wrap, lm_seq **out, size_t *bad_index);
+/* Stripe::stripe + configure_wrap from already encoded symbols */
+int lm_seq_from_symbols(lm_ctx *ctx, int alphabet, const uint8_t *sym, size_t n,
+                        size_t wrap, lm_seq **out);
+/* upload an existing host StripedSequence ([rows + wrap][stride]) */
+int lm_seq_from_striped(lm_ctx *ctx, int alphabet, const uint8_t *data,
+                        size_t rows, size_t wrap, size_t stride, size_t length,
+                        lm_seq **out);
+/* adopt caller-owned DEVICE memory holding [rows + wrap][32] bytes (16-byte
+ * aligned, row stride 32); the handle does not free it */
+int lm_seq_from_device(lm_ctx *ctx, int alphabet, void *device_ptr, size_t rows,
+                       size_t wrap, size_t length, lm_seq **out);
+/* benchmark input: counter-based synthetic sequence generated on the device
+ * (SURVEY.md 8d).  DNA: w = splitmix64(seed + (i >> 5)),
+ * sym(i) = (w >> 2(i & 31)) & 3; protein: (splitmix64(seed + i) >> 11) % 20.
+ * The handle holds the row slab [row_begin, row_begin + n_rows) (+ wrap rows)
+ * of the striped matrix of the whole `total_length`-symbol sequence, so each
+ * GPU of a sharded scan generates its own slab without any transfer; pass
+ * row_begin = 0, n_rows = ceil(total_length / 32) for the whole sequence. */
+int lm_seq_synthetic(lm_ctx *ctx, int alphabet, uint64_t seed,
+                     uint64_t total_length, uint64_t row_begin, uint64_t n_rows,
+                     size_t wrap, lm_seq **out);
+/* StripedSequence::configure_wrap on the device copy (only grows) */
+int lm_seq_configure_wrap(lm_ctx *ctx, lm_seq *seq, size_t wrap);
+int lm_seq_info(const lm_seq *seq, int *alphabet, size_t *rows, size_t *wrap,
+                size_t *length);
+void *lm_seq_device_ptr(const lm_seq *seq);
+/* copy [rows + wrap][32] back into dst ([rows + wrap][dst_stride]) */
+int lm_seq_download(lm_ctx *ctx, const lm_seq *seq, uint8_t *dst,
+                    size_t dst_stride);
+void lm_seq_free(lm_ctx *ctx, lm_seq *seq);
+
+/* Score::score_rows_into on a resident sequence.  `out` is a host pointer, or
+ * a device pointer when out_is_device != 0. */
+int lm_seq_score_f32(lm_ctx *ctx, const lm_seq *seq, const float *pssm,
+                     size_t m, size_t pssm_stride, size_t row_begin,
+                     size_t row_end, float *out, size_t out_stride,
+                     int out_is_device, size_t *out_rows);
+int lm_seq_score_u8(lm_ctx *ctx, const lm_seq *seq, const uint8_t *dm, size_t m,
+                    size_t dm_stride, size_t row_begin, size_t row_end,
+                    uint8_t *out, size_t out_stride, int out_is_device,
+                    size_t *out_rows);
+
+/* FUSED  ScoringMatrix::score (pwm/mod.rs:640-648) + StripedScores::argmax
+ * (scores.rs:190-192): scores never reach HBM.  Returns the cell the chosen
+ * reference back-end would return, bit-identical score.  `per_column`
+ * (nullable, [32]) and `first_cell` (nullable; score of cell (row_begin, 0))
+ * receive what lm_argmax_merge needs for multi-GPU merging.
+ * LM_EMPTY when length < m or the range is empty. */
+int lm_seq_score_argmax_f32(lm_ctx *ctx, const lm_seq *seq, const float *pssm,
+                            size_t m, size_t pssm_stride, size_t row_begin,
+                            size_t row_end, int rule, lm_hit *best,
+                            lm_colwin *per_column, float *first_cell);
+/* FUSED score + Threshold::threshold (scores.rs:207-213): all cells >= t of
+ * the scored rows, row-major order, exact f32 scores. */
+int lm_seq_score_threshold_f32(lm_ctx *ctx, const lm_seq *seq,
+                               const float *pssm, size_t m, size_t pssm_stride,
+                               size_t row_begin, size_t row_end, float t,
+                               lm_hit *hits, size_t cap, size_t *count);
+/* Many motifs over one resident sequence (the lightmotif-cli job loop,
+ * lightmotif-cli/src/main.rs:540-562): motif i is pssms[offsets[i] ..] with
+ * widths[i] rows of pssm_stride floats; best[i] as lm_seq_score_argmax_f32.
+ * The sequence needs wrap >= max(widths) - 1. */
+int lm_seq_score_argmax_f32_batch(lm_ctx *ctx, const lm_seq *seq,
+                                  const float *pssms, const uint32_t *widths,
+                                  const uint64_t *offsets, size_t n_motifs,
+                                  size_t pssm_stride, int rule, lm_hit *best);
+
+/* Merge per-column winners of `n_parts` consecutive row slabs (slab p scored
+ * rows [row_offsets[p], row_offsets[p+1])) into the cell the single-call
+ * argmax would return (multi-GPU reduce after an all-gather; host only).
+ * first_cell = score of cell (row_offsets[0], 0), needed by LM_RULE_AVX2.
+ * total_rows is the number of score rows used for `position`. */
+int lm_argmax_merge(const lm_colwin *parts, size_t n_parts,
+                    const uint64_t *row_offsets, float first_cell,
+                    uint64_t total_rows, int rule, lm_hit *best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTMOTIF_B200_H */

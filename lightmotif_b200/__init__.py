@@ -1,0 +1,389 @@
+"""lightmotif_b200 -- B200-native PWM scanning engine (drop-in for the
+``lightmotif::pli`` Score pipeline of althonos/lightmotif).
+
+The product is the CUDA library behind ``include/lightmotif_b200.h``; this
+package is the thin Python harness over that C ABI used by the tests and by
+``bench.py``.  The C++ host mirror of the reference's trait surface lives in
+``include/lightmotif_b200.hpp``.
+
+Nothing here computes scores on the CPU: every method forwards to the C ABI
+and raises if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import (DNA, PROTEIN, RULE_AVX2, RULE_GENERIC, RULE_SSE2, LANES, ColWin, Hit,
+                   LightmotifError)
+
+__all__ = ["Pipeline", "DeviceSequence", "InvalidSymbol", "UnsupportedBackend", "MatrixCoordinates",
+           "DNA", "PROTEIN", "RULE_GENERIC", "RULE_AVX2", "RULE_SSE2", "LANES", "alphabet_k",
+           "pad_pssm", "aligned_empty"]
+
+
+class InvalidSymbol(ValueError):
+    """lightmotif::err::InvalidSymbol(char), err.rs:10."""
+
+    def __init__(self, ch, index):
+        super().__init__(f"invalid symbol {ch!r} at index {index}")
+        self.ch, self.index = ch, index
+
+
+class UnsupportedBackend(RuntimeError):
+    """lightmotif::err::UnsupportedBackend, err.rs:34."""
+
+
+@dataclass(frozen=True)
+class MatrixCoordinates:
+    """dense.rs:28-39"""
+    row: int
+    col: int
+
+
+def alphabet_k(alphabet):
+    return 5 if alphabet == DNA else 21
+
+
+def aligned_empty(shape, dtype, align=64):
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    raw = np.empty(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def pad_pssm(pssm, alphabet, dtype=np.float32):
+    """Lay a [m, K] matrix out like DenseMatrix<T, K> (dense.rs:125-128): rows
+    padded to 32 bytes (stride 8 / 24 floats, 32 bytes for u8)."""
+    pssm = np.asarray(pssm, dtype=dtype)
+    m, k = pssm.shape
+    row_bytes = -(-(k * pssm.itemsize) // 32) * 32
+    stride = row_bytes // pssm.itemsize
+    out = np.zeros((m, stride), dtype=dtype)
+    out[:, :k] = pssm
+    return out, stride
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _hit(h):
+    return {"row": int(h.row), "col": int(h.col), "position": int(h.position), "score": float(np.float32(h.score))}
+
+
+class DeviceSequence:
+    """A striped sequence resident in HBM (lm_seq handle)."""
+
+    def __init__(self, pli, handle):
+        self._pli, self._h = pli, handle
+        a, r, w, n = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        capi.lib().lm_seq_info(handle, C.byref(a), C.byref(r), C.byref(w), C.byref(n))
+        self.alphabet, self.rows, self.wrap, self.length = a.value, r.value, w.value, n.value
+
+    def _refresh(self):
+        self.__init__(self._pli, self._h)
+
+    def configure_wrap(self, wrap):
+        self._pli._check(capi.lib().lm_seq_configure_wrap(self._pli._ctx, self._h, wrap))
+        self._refresh()
+
+    def configure(self, pssm):
+        """StripedSequence::configure (seq.rs:362-366)."""
+        if len(pssm):
+            self.configure_wrap(len(pssm) - 1)
+
+    def download(self):
+        out = aligned_empty((self.rows + self.wrap, LANES), np.uint8)
+        self._pli._check(capi.lib().lm_seq_download(self._pli._ctx, self._h, _ptr(out), LANES))
+        return out
+
+    @property
+    def device_ptr(self):
+        return capi.lib().lm_seq_device_ptr(self._h)
+
+    def free(self):
+        if self._h:
+            capi.lib().lm_seq_free(self._pli._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- scoring ------------------------------------------------------
+    def _rng(self, rows):
+        return (0, self.rows) if rows is None else (rows[0], rows[1])
+
+    def score(self, pssm, rows=None, out=None):
+        """Score::score_rows_into -> [n, 32] f32 (or u8 for a u8 matrix)."""
+        pssm = np.asarray(pssm)
+        is_u8 = pssm.dtype == np.uint8
+        p, stride = pad_pssm(pssm, self.alphabet, np.uint8 if is_u8 else np.float32)
+        b, e = self._rng(rows)
+        n = max(e - b, 0)
+        if out is None:
+            out = aligned_empty((n, LANES), np.uint8 if is_u8 else np.float32)
+        got = C.c_size_t(0)
+        fn = capi.lib().lm_seq_score_u8 if is_u8 else capi.lib().lm_seq_score_f32
+        self._pli._check(fn(self._pli._ctx, self._h, _ptr(p), p.shape[0], stride, b, e, _ptr(out), LANES, 0,
+                            C.byref(got)))
+        return out[:got.value]
+
+    def score_into_device(self, pssm, device_ptr, out_stride=LANES, rows=None):
+        pssm = np.asarray(pssm)
+        is_u8 = pssm.dtype == np.uint8
+        p, stride = pad_pssm(pssm, self.alphabet, np.uint8 if is_u8 else np.float32)
+        b, e = self._rng(rows)
+        got = C.c_size_t(0)
+        fn = capi.lib().lm_seq_score_u8 if is_u8 else capi.lib().lm_seq_score_f32
+        self._pli._check(fn(self._pli._ctx, self._h, _ptr(p), p.shape[0], stride, b, e, C.c_void_p(device_ptr),
+                            out_stride, 1, C.byref(got)))
+        return got.value
+
+    def score_argmax(self, pssm, rows=None, rule=RULE_AVX2, with_columns=False):
+        """Fused ScoringMatrix::score + StripedScores::argmax."""
+        p, stride = pad_pssm(pssm, self.alphabet)
+        b, e = self._rng(rows)
+        best = Hit()
+        cols = (ColWin * LANES)()
+        fc = C.c_float(0)
+        st = capi.lib().lm_seq_score_argmax_f32(self._pli._ctx, self._h, _ptr(p), p.shape[0], stride, b, e, rule,
+                                                C.byref(best), cols, C.byref(fc))
+        self._pli._check(st)
+        if st == capi.EMPTY:
+            return None
+        res = _hit(best)
+        if with_columns:
+            res["columns"] = [(int(c.row), float(np.float32(c.score)), int(c.valid)) for c in cols]
+            res["first_cell"] = float(np.float32(fc.value))
+        return res
+
+    def score_threshold(self, pssm, t, rows=None, cap=1 << 20):
+        """Fused score + Threshold::threshold -> list of hits in row-major order."""
+        p, stride = pad_pssm(pssm, self.alphabet)
+        b, e = self._rng(rows)
+        hits = (Hit * cap)()
+        count = C.c_size_t(0)
+        st = capi.lib().lm_seq_score_threshold_f32(self._pli._ctx, self._h, _ptr(p), p.shape[0], stride, b, e,
+                                                   float(t), hits, cap, C.byref(count))
+        if st == capi.ERR_OVERFLOW:
+            return self.score_threshold(pssm, t, rows, cap=count.value)
+        self._pli._check(st)
+        return [_hit(hits[i]) for i in range(count.value)]
+
+    def score_argmax_batch(self, pssms, rule=RULE_AVX2):
+        """Many motifs over this sequence (the lightmotif-cli job loop)."""
+        k = alphabet_k(self.alphabet)
+        stride = pad_pssm(np.zeros((1, k), np.float32), self.alphabet)[1]
+        widths = np.array([len(p) for p in pssms], dtype=np.uint32)
+        offs = np.zeros(len(pssms), dtype=np.uint64)
+        flat = np.zeros((int(widths.sum()), stride), dtype=np.float32)
+        at = 0
+        for i, p in enumerate(pssms):
+            offs[i] = at * stride
+            flat[at:at + len(p), :k] = np.asarray(p, dtype=np.float32)
+            at += len(p)
+        best = (Hit * len(pssms))()
+        self._pli._check(capi.lib().lm_seq_score_argmax_f32_batch(
+            self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs), len(pssms), stride, rule, best))
+        return [_hit(b) for b in best]
+
+
+class Pipeline:
+    """``Pipeline::<A, Cuda>::cuda()``: the CUDA back-end of the pipeline traits
+    (Encode / Stripe / Score / Maximum / Threshold, pli/mod.rs:34-222)."""
+
+    def __init__(self, alphabet=DNA, device=0, stream=None):
+        self.alphabet = alphabet
+        ctx = C.c_void_p()
+        if stream is None:
+            st = capi.lib().lm_ctx_create(device, C.byref(ctx))
+        else:
+            st = capi.lib().lm_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(ctx))
+        if st == capi.ERR_UNSUPPORTED:
+            raise UnsupportedBackend("no sm_100 CUDA device")
+        if st != capi.OK:
+            raise LightmotifError(st)
+        self._ctx = ctx
+
+    @classmethod
+    def cuda(cls, alphabet=DNA, device=0, stream=None):
+        return cls(alphabet, device, stream)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            capi.lib().lm_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status):
+        if status < 0:
+            raise LightmotifError(status, capi.lib().lm_ctx_last_error(self._ctx).decode())
+        return status
+
+    @property
+    def kernel_launches(self):
+        return capi.lib().lm_ctx_kernel_launches(self._ctx)
+
+    @property
+    def last_kernel_ms(self):
+        return capi.lib().lm_ctx_last_kernel_ms(self._ctx)
+
+    @property
+    def stream(self):
+        return capi.lib().lm_ctx_stream(self._ctx)
+
+    def synchronize(self):
+        self._check(capi.lib().lm_ctx_synchronize(self._ctx))
+
+    # ---- Encode ---------------------------------------------------------
+    @staticmethod
+    def _bytes(seq):
+        if isinstance(seq, str):
+            seq = seq.encode("ascii")
+        if isinstance(seq, (bytes, bytearray)):
+            return np.frombuffer(bytes(seq), dtype=np.uint8)
+        return np.ascontiguousarray(seq, dtype=np.uint8)
+
+    def encode(self, seq):
+        a = self._bytes(seq)
+        dst = np.empty(a.size, dtype=np.uint8)
+        bad = C.c_size_t(0)
+        st = capi.lib().lm_encode(self._ctx, self.alphabet, _ptr(a), a.size, _ptr(dst), C.byref(bad))
+        if st == capi.ERR_INVALID_SYMBOL:
+            raise InvalidSymbol(chr(int(a[bad.value])), bad.value)
+        self._check(st)
+        return dst
+
+    def encode_lossy(self, seq):
+        a = self._bytes(seq)
+        dst = np.empty(a.size, dtype=np.uint8)
+        self._check(capi.lib().lm_encode_lossy(self._ctx, self.alphabet, _ptr(a), a.size, _ptr(dst)))
+        return dst
+
+    # ---- Stripe ---------------------------------------------------------
+    def stripe(self, sym, wrap=0):
+        """Stripe::stripe (+ configure_wrap) on host buffers -> [rows + wrap, 32]."""
+        sym = np.ascontiguousarray(sym, dtype=np.uint8)
+        rows = -(-sym.size // LANES)
+        data = aligned_empty((rows + wrap, LANES), np.uint8)
+        data[rows:] = 255
+        self._check(capi.lib().lm_stripe(self._ctx, self.alphabet, _ptr(sym), sym.size, _ptr(data), LANES))
+        if wrap:
+            self._check(capi.lib().lm_configure_wrap(self._ctx, self.alphabet, _ptr(data), rows, LANES, wrap))
+        return data
+
+    # ---- Score (host buffers) --------------------------------------------
+    def score_rows(self, pssm, striped, length, wrap, rows=None):
+        pssm = np.asarray(pssm)
+        is_u8 = pssm.dtype == np.uint8
+        p, stride = pad_pssm(pssm, self.alphabet, np.uint8 if is_u8 else np.float32)
+        nrows = striped.shape[0] - wrap
+        b, e = (0, nrows) if rows is None else rows
+        out = aligned_empty((max(e - b, 0), LANES), np.uint8 if is_u8 else np.float32)
+        got = C.c_size_t(0)
+        fn = capi.lib().lm_score_u8_rows if is_u8 else capi.lib().lm_score_f32_rows
+        self._check(fn(self._ctx, self.alphabet, _ptr(p), p.shape[0], stride, _ptr(striped), nrows, wrap,
+                       striped.strides[0], length, b, e, _ptr(out), LANES, C.byref(got)))
+        return out[:got.value]
+
+    # ---- Maximum / Threshold (host score matrices) -------------------------
+    def argmax(self, scores, rule=RULE_AVX2):
+        best = Hit()
+        is_u8 = scores.dtype == np.uint8
+        fn = capi.lib().lm_argmax_u8 if is_u8 else capi.lib().lm_argmax_f32
+        st = self._check(fn(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0] // scores.itemsize, rule,
+                            C.byref(best)))
+        return None if st == capi.EMPTY else MatrixCoordinates(int(best.row), int(best.col))
+
+    def max(self, scores):
+        is_u8 = scores.dtype == np.uint8
+        out = C.c_uint8(0) if is_u8 else C.c_float(0)
+        fn = capi.lib().lm_max_u8 if is_u8 else capi.lib().lm_max_f32
+        st = self._check(fn(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0] // scores.itemsize,
+                            C.byref(out)))
+        return None if st == capi.EMPTY else (int(out.value) if is_u8 else np.float32(out.value))
+
+    def threshold(self, scores, t, cap=None):
+        is_u8 = scores.dtype == np.uint8
+        cap = cap or max(scores.size, 1)
+        hits = (Hit * cap)()
+        count = C.c_size_t(0)
+        if is_u8:
+            st = capi.lib().lm_threshold_u8(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0], int(t),
+                                            hits, cap, C.byref(count))
+        else:
+            st = capi.lib().lm_threshold_f32(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0] // 4,
+                                             float(t), hits, cap, C.byref(count))
+        self._check(st)
+        return [MatrixCoordinates(int(hits[i].row), int(hits[i].col)) for i in range(count.value)]
+
+    # ---- device-resident sequences ----------------------------------------
+    def _seq(self, handle):
+        return DeviceSequence(self, handle)
+
+    def sequence_from_ascii(self, seq, wrap=0, lossy=False):
+        a = self._bytes(seq)
+        h = C.c_void_p()
+        bad = C.c_size_t(0)
+        st = capi.lib().lm_seq_from_ascii(self._ctx, self.alphabet, _ptr(a), a.size, int(lossy), wrap, C.byref(h),
+                                          C.byref(bad))
+        if st == capi.ERR_INVALID_SYMBOL:
+            raise InvalidSymbol(chr(int(a[bad.value])), bad.value)
+        self._check(st)
+        return self._seq(h)
+
+    def sequence_from_symbols(self, sym, wrap=0):
+        sym = np.ascontiguousarray(sym, dtype=np.uint8)
+        h = C.c_void_p()
+        self._check(capi.lib().lm_seq_from_symbols(self._ctx, self.alphabet, _ptr(sym), sym.size, wrap, C.byref(h)))
+        return self._seq(h)
+
+    def sequence_from_striped(self, data, length, wrap):
+        h = C.c_void_p()
+        rows = data.shape[0] - wrap
+        self._check(capi.lib().lm_seq_from_striped(self._ctx, self.alphabet, _ptr(data), rows, wrap,
+                                                   data.strides[0], length, C.byref(h)))
+        return self._seq(h)
+
+    def sequence_from_device(self, device_ptr, rows, wrap, length):
+        h = C.c_void_p()
+        self._check(capi.lib().lm_seq_from_device(self._ctx, self.alphabet, C.c_void_p(device_ptr), rows, wrap,
+                                                  length, C.byref(h)))
+        return self._seq(h)
+
+    def sequence_synthetic(self, total_length, wrap, seed=0x5EED, row_begin=0, n_rows=None):
+        rows_global = -(-total_length // LANES)
+        if n_rows is None:
+            n_rows = rows_global - row_begin
+        h = C.c_void_p()
+        self._check(capi.lib().lm_seq_synthetic(self._ctx, self.alphabet, seed, total_length, row_begin, n_rows,
+                                                wrap, C.byref(h)))
+        return self._seq(h)
+
+
+def argmax_merge(parts, row_offsets, first_cell, total_rows, rule=RULE_AVX2):
+    """lm_argmax_merge: parts = list (one per slab) of 32 (row, score, valid)."""
+    n = len(parts)
+    arr = (ColWin * (n * LANES))()
+    for p, cols in enumerate(parts):
+        for c, (row, score, valid) in enumerate(cols):
+            arr[p * LANES + c] = ColWin(int(row), float(score), int(valid))
+    offs = np.asarray(row_offsets, dtype=np.uint64)
+    best = Hit()
+    st = capi.lib().lm_argmax_merge(arr, n, _ptr(offs), float(first_cell), int(total_rows), rule, C.byref(best))
+    if st < 0:
+        raise LightmotifError(st)
+    return None if st == capi.EMPTY else _hit(best)

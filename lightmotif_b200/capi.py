@@ -1,0 +1,120 @@
+"""ctypes bindings of the C ABI (include/lightmotif_b200.h).
+
+The shared library is built in-tree by ``lightmotif_b200/build.py`` (nvcc,
+sm_100a).  Importing this module FAILS LOUDLY when the library is missing:
+there is no CPU fall-back anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "liblightmotif_b200.so"
+
+LANES = 32
+OK, EMPTY = 0, 1
+ERR_INVALID_ARG, ERR_INVALID_SYMBOL, ERR_WRAP, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_OVERFLOW = (
+    -1, -2, -3, -4, -5, -6, -7)
+DNA, PROTEIN = 0, 1
+RULE_GENERIC, RULE_AVX2, RULE_SSE2 = 0, 1, 2
+
+
+class Hit(C.Structure):
+    _fields_ = [("row", C.c_uint64), ("position", C.c_uint64), ("col", C.c_uint32), ("score", C.c_float)]
+
+
+class ColWin(C.Structure):
+    _fields_ = [("row", C.c_uint64), ("score", C.c_float), ("valid", C.c_uint32)]
+
+
+class LightmotifError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        msg = lib().lm_strerror(status).decode()
+        super().__init__(f"{msg} (status {status})" + (f": {detail}" if detail else ""))
+
+
+_lib = None
+
+# every symbol declared in include/lightmotif_b200.h
+SYMBOLS = [
+    "lm_abi_version", "lm_strerror", "lm_ctx_last_error", "lm_ctx_create", "lm_ctx_create_on_stream",
+    "lm_ctx_destroy", "lm_ctx_stream", "lm_ctx_synchronize", "lm_ctx_kernel_launches",
+    "lm_ctx_last_kernel_ms", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
+    "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_argmax_u8", "lm_max_u8",
+    "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
+    "lm_seq_from_striped", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
+    "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
+    "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_threshold_f32",
+    "lm_seq_score_argmax_f32_batch", "lm_argmax_merge",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m lightmotif_b200.build` "
+                "(nvcc, sm_100a). lightmotif_b200 has no CPU fall-back.")
+        _lib = C.CDLL(str(LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    sz, vp, i = C.c_size_t, C.c_void_p, C.c_int
+    u8p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    szp = C.POINTER(sz)
+    hitp, cwp = C.POINTER(Hit), C.POINTER(ColWin)
+    L.lm_abi_version.restype = i
+    L.lm_strerror.argtypes = [i]
+    L.lm_strerror.restype = C.c_char_p
+    L.lm_ctx_last_error.argtypes = [vp]
+    L.lm_ctx_last_error.restype = C.c_char_p
+    L.lm_ctx_create.argtypes = [i, C.POINTER(vp)]
+    L.lm_ctx_create_on_stream.argtypes = [i, vp, C.POINTER(vp)]
+    L.lm_ctx_destroy.argtypes = [vp]
+    L.lm_ctx_destroy.restype = None
+    L.lm_ctx_stream.argtypes = [vp]
+    L.lm_ctx_stream.restype = vp
+    L.lm_ctx_synchronize.argtypes = [vp]
+    L.lm_ctx_kernel_launches.argtypes = [vp]
+    L.lm_ctx_kernel_launches.restype = C.c_uint64
+    L.lm_ctx_last_kernel_ms.argtypes = [vp]
+    L.lm_ctx_last_kernel_ms.restype = C.c_float
+    L.lm_encode.argtypes = [vp, i, vp, sz, vp, szp]
+    L.lm_encode_lossy.argtypes = [vp, i, vp, sz, vp]
+    L.lm_stripe.argtypes = [vp, i, vp, sz, vp, sz]
+    L.lm_configure_wrap.argtypes = [vp, i, vp, sz, sz, sz]
+    L.lm_score_f32_rows.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, sz, sz, sz, sz, vp, sz, szp]
+    L.lm_score_u8_rows.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, sz, sz, sz, sz, vp, sz, szp]
+    L.lm_argmax_f32.argtypes = [vp, vp, sz, sz, i, hitp]
+    L.lm_argmax_u8.argtypes = [vp, vp, sz, sz, i, hitp]
+    L.lm_max_f32.argtypes = [vp, vp, sz, sz, f32p]
+    L.lm_max_u8.argtypes = [vp, vp, sz, sz, u8p]
+    L.lm_threshold_f32.argtypes = [vp, vp, sz, sz, C.c_float, hitp, sz, szp]
+    L.lm_threshold_u8.argtypes = [vp, vp, sz, sz, C.c_uint8, hitp, sz, szp]
+    L.lm_seq_from_ascii.argtypes = [vp, i, vp, sz, i, sz, C.POINTER(vp), szp]
+    L.lm_seq_from_symbols.argtypes = [vp, i, vp, sz, sz, C.POINTER(vp)]
+    L.lm_seq_from_striped.argtypes = [vp, i, vp, sz, sz, sz, sz, C.POINTER(vp)]
+    L.lm_seq_from_device.argtypes = [vp, i, vp, sz, sz, sz, C.POINTER(vp)]
+    L.lm_seq_synthetic.argtypes = [vp, i, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, sz, C.POINTER(vp)]
+    L.lm_seq_configure_wrap.argtypes = [vp, vp, sz]
+    L.lm_seq_info.argtypes = [vp, C.POINTER(i), szp, szp, szp]
+    L.lm_seq_device_ptr.argtypes = [vp]
+    L.lm_seq_device_ptr.restype = vp
+    L.lm_seq_download.argtypes = [vp, vp, vp, sz]
+    L.lm_seq_free.argtypes = [vp, vp]
+    L.lm_seq_free.restype = None
+    L.lm_seq_score_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, vp, sz, i, szp]
+    L.lm_seq_score_u8.argtypes = [vp, vp, vp, sz, sz, sz, sz, vp, sz, i, szp]
+    L.lm_seq_score_argmax_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, i, hitp, cwp, f32p]
+    L.lm_seq_score_threshold_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, C.c_float, hitp, sz, szp]
+    L.lm_seq_score_argmax_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, hitp]
+    L.lm_argmax_merge.argtypes = [cwp, sz, vp, C.c_float, C.c_uint64, i, hitp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("lm_abi_version",):
+            pass

@@ -1,0 +1,946 @@
+// capi.cu -- the extern "C" boundary (include/lightmotif_b200.h): contexts,
+// device-resident sequence handles, host<->device plumbing and the tiny host
+// finishing steps (tie rules over 32 per-column winners, hit ordering).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "reduce.cuh"
+#include "score.cuh"
+#include "seqops.cuh"
+
+using namespace lm;
+
+// ------------------------------------------------------------------ context
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct lm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  float last_ms = 0.f;
+  uint64_t launches = 0;
+  char err[256] = {0};
+  DevBuf d_in, d_out, d_table, d_small, d_hits;  // device scratch, grown on demand
+  void* h_pin = nullptr;                          // pinned host staging
+  size_t h_pin_bytes = 0;
+};
+
+struct lm_seq {
+  int alphabet = 0;
+  int device = 0;
+  uint8_t* data = nullptr;  // [alloc_rows][32]
+  bool owned = true;
+  size_t rows = 0, wrap = 0, length = 0, alloc_rows = 0;
+};
+
+namespace {
+
+constexpr size_t SLACK_ROWS = 64;      // readable rows kept behind rows + wrap
+constexpr size_t SMALL_BYTES = 1 << 20;  // keys / counters block
+
+int fail(lm_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();  // clear sticky-free errors
+  return e == cudaErrorMemoryAllocation ? LM_ERR_OOM : LM_ERR_CUDA;
+}
+
+#define LM_TRY(expr)                                      \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return fail(ctx, _e, #expr);   \
+  } while (0)
+
+#define LM_CHECK(expr)          \
+  do {                          \
+    int _s = (expr);            \
+    if (_s < 0) return _s;      \
+  } while (0)
+
+int ensure(lm_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return LM_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  size_t want = std::max<size_t>(bytes, 4096);
+  LM_TRY(cudaMalloc(&b.p, want));
+  b.bytes = want;
+  return LM_OK;
+}
+
+int ensure_pinned(lm_ctx* ctx, size_t bytes) {
+  if (ctx->h_pin_bytes >= bytes && ctx->h_pin) return LM_OK;
+  if (ctx->h_pin) { cudaFreeHost(ctx->h_pin); ctx->h_pin = nullptr; ctx->h_pin_bytes = 0; }
+  size_t want = std::max<size_t>(bytes, 1 << 16);
+  LM_TRY(cudaHostAlloc(&ctx->h_pin, want, cudaHostAllocDefault));
+  ctx->h_pin_bytes = want;
+  return LM_OK;
+}
+
+int bind(lm_ctx* ctx) {
+  if (!ctx) return LM_ERR_INVALID_ARG;
+  LM_TRY(cudaSetDevice(ctx->device));
+  return LM_OK;
+}
+
+void timer_begin(lm_ctx* ctx) { cudaEventRecord(ctx->ev0, ctx->stream); }
+void timer_end(lm_ctx* ctx) {
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  ctx->timed = true;
+}
+
+bool valid_alphabet(int a) { return a == LM_DNA || a == LM_PROTEIN; }
+uint8_t pad_symbol(int a) { return (uint8_t)(alphabet_k(a) - 1); }
+
+// Build the kernel look-up table [m_pad][KP] (32-bit words) from a PSSM.
+// Columns >= K are zero-filled and never indexed; rows >= m are +0.0 / 0.
+void build_table_f32(int alphabet, const float* pssm, size_t m, size_t stride, uint32_t* dst) {
+  const int kp = table_kp(alphabet), k = alphabet_k(alphabet), mp = table_mpad(m);
+  std::memset(dst, 0, (size_t)mp * kp * 4);
+  for (size_t j = 0; j < m; ++j)
+    for (int s = 0; s < k; ++s) std::memcpy(&dst[j * kp + s], &pssm[j * stride + s], 4);
+}
+void build_table_u8(int alphabet, const uint8_t* dm, size_t m, size_t stride, uint32_t* dst) {
+  const int kp = table_kp(alphabet), k = alphabet_k(alphabet), mp = table_mpad(m);
+  std::memset(dst, 0, (size_t)mp * kp * 4);
+  for (size_t j = 0; j < m; ++j)
+    for (int s = 0; s < k; ++s) dst[j * kp + s] = dm[j * stride + s];
+}
+
+struct ColKeys {
+  unsigned long long keys[32];
+  uint32_t first_cell;
+};
+
+void decode_colwins(const unsigned long long* keys, bool is_u8, lm_colwin* out) {
+  for (int c = 0; c < 32; ++c) {
+    unsigned long long k = keys[c];
+    out[c].valid = k != 0;
+    out[c].row = (uint32_t)(k & 0xffffffffull);
+    uint32_t sk = (uint32_t)(k >> 32);
+    out[c].score = k == 0 ? 0.f : (is_u8 ? (float)(sk - 1u) : key_to_f32(sk));
+  }
+}
+
+// Apply a reference back-end's tie rule to 32 per-column winners (each the
+// column maximum with the LAST row attaining it).  first_cell = score of
+// cell (0, 0) of the scored range.  Returns LM_EMPTY when nothing is valid.
+int apply_rule(const lm_colwin* cw, float first_cell, int rule, bool is_u8, uint64_t total_rows,
+               uint64_t row_base, lm_hit* best) {
+  int bc = -1;
+  uint64_t br = 0;
+  float bs = 0.f;
+  bool any = false;
+  for (int c = 0; c < 32; ++c) any = any || cw[c].valid;
+  if (!any) return LM_EMPTY;
+  if (rule == LM_RULE_GENERIC) {
+    // pli/mod.rs:140-152: row-major scan with `>=`: highest score, then the
+    // largest row, then the largest column
+    for (int c = 0; c < 32; ++c) {
+      if (!cw[c].valid) continue;
+      if (bc < 0 || cw[c].score > bs || (cw[c].score == bs && cw[c].row >= br)) {
+        bc = c; br = cw[c].row; bs = cw[c].score;
+      }
+    }
+  } else if (rule == LM_RULE_AVX2 && !is_u8) {
+    // avx2.rs:411-421: start from cell (0,0), strict `>` over columns 0..31
+    bc = 0; br = row_base; bs = first_cell;
+    for (int c = 0; c < 32; ++c)
+      if (cw[c].valid && cw[c].score > bs) { bc = c; br = cw[c].row; bs = cw[c].score; }
+  } else if (rule == LM_RULE_SSE2 && !is_u8) {
+    // sse2.rs:246-258: start from (0,0), `>=` over columns => last column wins
+    bc = 0; br = row_base; bs = first_cell;
+    for (int c = 0; c < 32; ++c)
+      if (cw[c].valid && cw[c].score >= bs) { bc = c; br = cw[c].row; bs = cw[c].score; }
+  } else {
+    // u8: avx2.rs:525-528 Iterator::max_by_key => last column among equal maxima;
+    // SSE2 has no u8 argmax and falls back to the generic scan
+    if (rule == LM_RULE_SSE2) return apply_rule(cw, first_cell, LM_RULE_GENERIC, is_u8, total_rows, row_base, best);
+    for (int c = 0; c < 32; ++c)
+      if (cw[c].valid && (bc < 0 || cw[c].score >= bs)) { bc = c; br = cw[c].row; bs = cw[c].score; }
+  }
+  best->row = br;
+  best->col = (uint32_t)bc;
+  best->score = bs;
+  best->position = (uint64_t)bc * total_rows + br;
+  return LM_OK;
+}
+
+float bits_to_score(uint32_t bits, bool is_u8) {
+  if (is_u8) return (float)bits;
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+
+void sort_hits(lm_hit* hits, size_t n) {
+  std::sort(hits, hits + n, [](const lm_hit& a, const lm_hit& b) {
+    return a.row != b.row ? a.row < b.row : a.col < b.col;
+  });
+}
+
+// shared argument validation for scoring calls; returns LM_OK, LM_EMPTY
+// (nothing to score: the reference resizes to (0, 0)) or an error
+int check_score_args(size_t m, size_t rows, size_t wrap, size_t length, size_t row_begin,
+                     size_t row_end) {
+  if (m == 0) return LM_ERR_INVALID_ARG;
+  if (wrap + 1 < m) return LM_ERR_WRAP;             // avx2.rs:832-837
+  if (length < m || row_end <= row_begin) return LM_EMPTY;  // pli/mod.rs:85-88
+  if (row_end > rows) return LM_ERR_INVALID_ARG;
+  if (rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;  // 32-bit rows in packed keys
+  return LM_OK;
+}
+
+int upload_table(lm_ctx* ctx, int alphabet, const void* pssm, size_t m, size_t stride, bool is_u8) {
+  const size_t bytes = (size_t)table_mpad(m) * table_kp(alphabet) * 4;
+  LM_CHECK(ensure_pinned(ctx, bytes));
+  LM_CHECK(ensure(ctx, ctx->d_table, bytes));
+  if (is_u8) build_table_u8(alphabet, (const uint8_t*)pssm, m, stride, (uint32_t*)ctx->h_pin);
+  else build_table_f32(alphabet, (const float*)pssm, m, stride, (uint32_t*)ctx->h_pin);
+  LM_TRY(cudaMemcpyAsync(ctx->d_table.p, ctx->h_pin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // the pinned buffer is reused by the next call: make sure the copy has left it
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+int limits_ok(int alphabet, size_t m) {
+  // shared-memory budget of score.cu (table + tile buffers <= 200 KB)
+  size_t mp = table_mpad(m);
+  size_t total = mp * table_kp(alphabet) * 4 + (128 + mp) * (32 * 3 + 4) + 4096;
+  return total <= 200 * 1024 ? LM_OK : LM_ERR_UNSUPPORTED;
+}
+
+// core: score rows [row_begin, row_end) of device matrix `seq` with the table
+// already uploaded to ctx->d_table
+int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* seq, size_t avail_rows,
+              size_t m, size_t row_begin, size_t row_end, void* d_out, size_t out_stride,
+              float thr_f32, uint8_t thr_u8, lm_hit* d_hits, size_t cap) {
+  ScoreArgs a;
+  a.seq = seq;
+  a.avail_rows = avail_rows;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  a.pad_sym = pad_symbol(alphabet);
+  a.tables = (const uint32_t*)ctx->d_table.p;
+  a.m_pad = table_mpad(m);
+  a.n_motifs = 1;
+  a.out = d_out;
+  a.out_stride = out_stride;
+  uint8_t* small = (uint8_t*)ctx->d_small.p;
+  a.colkeys = (unsigned long long*)small;
+  a.first_cell = (uint32_t*)(small + 256);
+  a.count = (unsigned long long*)(small + 264);
+  if (is_u8) a.thr_bits = thr_u8; else std::memcpy(&a.thr_bits, &thr_f32, 4);
+  a.hits = d_hits;
+  a.cap = cap;
+  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_score(alphabet, mode, is_u8, a, ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  return LM_OK;
+}
+
+int fetch_colkeys(lm_ctx* ctx, ColKeys* out) {
+  LM_TRY(cudaMemcpyAsync(out, ctx->d_small.p, sizeof(ColKeys), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+int seq_alloc(lm_ctx* ctx, int alphabet, size_t rows, size_t wrap, size_t length, lm_seq** out) {
+  lm_seq* s = new (std::nothrow) lm_seq();
+  if (!s) return LM_ERR_OOM;
+  s->alphabet = alphabet;
+  s->device = ctx->device;
+  s->rows = rows;
+  s->wrap = wrap;
+  s->length = length;
+  s->alloc_rows = rows + wrap + SLACK_ROWS;
+  cudaError_t e = cudaMalloc((void**)&s->data, s->alloc_rows * 32);
+  if (e != cudaSuccess) { delete s; return fail(ctx, e, "cudaMalloc(sequence)"); }
+  *out = s;
+  return LM_OK;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------- lifecycle
+
+extern "C" {
+
+int lm_abi_version(void) { return LM_ABI_VERSION; }
+
+const char* lm_strerror(int status) {
+  switch (status) {
+    case LM_OK: return "ok";
+    case LM_EMPTY: return "empty (None)";
+    case LM_ERR_INVALID_ARG: return "invalid argument";
+    case LM_ERR_INVALID_SYMBOL: return "invalid symbol in sequence";
+    case LM_ERR_WRAP: return "not enough wrapping rows for motif";
+    case LM_ERR_CUDA: return "CUDA error";
+    case LM_ERR_OOM: return "out of memory";
+    case LM_ERR_UNSUPPORTED: return "unsupported backend or size";
+    case LM_ERR_OVERFLOW: return "output buffer too small";
+    default: return "unknown status";
+  }
+}
+
+const char* lm_ctx_last_error(const lm_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+int lm_ctx_create_on_stream(int device, void* cuda_stream, lm_ctx** out) {
+  if (!out) return LM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    cudaGetLastError();
+    return LM_ERR_UNSUPPORTED;  // err.rs:34 UnsupportedBackend
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LM_ERR_UNSUPPORTED;
+  if (prop.major < 10) return LM_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
+  lm_ctx* ctx = new (std::nothrow) lm_ctx();
+  if (!ctx) return LM_ERR_OOM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  auto bail = [&](cudaError_t e, const char* w) { int s = fail(ctx, e, w); lm_ctx_destroy(ctx); return s; };
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return bail(e, "cudaSetDevice");
+  if (cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+  } else {
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail(e, "cudaStreamCreate");
+    ctx->own_stream = true;
+  }
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  int s = ensure(ctx, ctx->d_small, SMALL_BYTES);
+  if (s < 0) { lm_ctx_destroy(ctx); return s; }
+  *out = ctx;
+  return LM_OK;
+}
+
+int lm_ctx_create(int device, lm_ctx** out) { return lm_ctx_create_on_stream(device, nullptr, out); }
+
+void lm_ctx_destroy(lm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_small, &ctx->d_hits})
+    if (b->p) cudaFree(b->p);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* lm_ctx_stream(lm_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int lm_ctx_synchronize(lm_ctx* ctx) {
+  LM_CHECK(bind(ctx));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+uint64_t lm_ctx_kernel_launches(const lm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+float lm_ctx_last_kernel_ms(const lm_ctx* ctx) {
+  if (!ctx || !ctx->timed) return 0.f;
+  lm_ctx* c = const_cast<lm_ctx*>(ctx);
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.f;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return 0.f;
+  c->last_ms = ms;
+  return ms;
+}
+
+// ----------------------------------------------- host-buffer trait mirrors
+
+static int encode_impl(lm_ctx* ctx, int alphabet, const uint8_t* ascii, size_t n, uint8_t* dst,
+                       size_t* bad_index, bool lossy) {
+  LM_CHECK(bind(ctx));
+  if (!valid_alphabet(alphabet) || (n && (!ascii || !dst))) return LM_ERR_INVALID_ARG;
+  if (n == 0) return LM_OK;
+  LM_CHECK(ensure(ctx, ctx->d_in, n));
+  LM_CHECK(ensure(ctx, ctx->d_out, n));
+  unsigned long long* d_bad = (unsigned long long*)ctx->d_small.p;
+  LM_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(ctx->d_in.p, ascii, n, cudaMemcpyHostToDevice, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_encode((const uint8_t*)ctx->d_in.p, n, (uint8_t*)ctx->d_out.p, alphabet, d_bad,
+                       ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  unsigned long long bad = 0;
+  LM_TRY(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(dst, ctx->d_out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  if (!lossy && bad != ~0ull) {
+    if (bad_index) *bad_index = (size_t)bad;
+    return LM_ERR_INVALID_SYMBOL;
+  }
+  return LM_OK;
+}
+
+int lm_encode(lm_ctx* ctx, int alphabet, const uint8_t* ascii, size_t n, uint8_t* dst,
+              size_t* bad_index) {
+  return encode_impl(ctx, alphabet, ascii, n, dst, bad_index, false);
+}
+
+int lm_encode_lossy(lm_ctx* ctx, int alphabet, const uint8_t* ascii, size_t n, uint8_t* dst) {
+  return encode_impl(ctx, alphabet, ascii, n, dst, nullptr, true);
+}
+
+int lm_stripe(lm_ctx* ctx, int alphabet, const uint8_t* sym, size_t n, uint8_t* dst,
+              size_t dst_stride) {
+  LM_CHECK(bind(ctx));
+  if (!valid_alphabet(alphabet) || (n && (!sym || !dst)) || dst_stride < 32) return LM_ERR_INVALID_ARG;
+  if (n == 0) return LM_OK;
+  const size_t rows = (n + 31) / 32;
+  LM_CHECK(ensure(ctx, ctx->d_in, n));
+  LM_CHECK(ensure(ctx, ctx->d_out, rows * 32));
+  LM_TRY(cudaMemcpyAsync(ctx->d_in.p, sym, n, cudaMemcpyHostToDevice, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_stripe((const uint8_t*)ctx->d_in.p, false, n, rows, 0, rows, (uint8_t*)ctx->d_out.p,
+                       alphabet, nullptr, ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  LM_TRY(cudaMemcpy2DAsync(dst, dst_stride, ctx->d_out.p, 32, 32, rows, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+int lm_configure_wrap(lm_ctx* ctx, int alphabet, uint8_t* data, size_t rows, size_t stride,
+                      size_t wrap) {
+  LM_CHECK(bind(ctx));
+  if (!valid_alphabet(alphabet) || !data || stride < 32) return LM_ERR_INVALID_ARG;
+  if (wrap == 0) return LM_OK;
+  // the wrap rows only depend on the first min(rows, wrap) base rows; the
+  // device works on a compact copy [base | wrap] of those
+  const size_t base = std::min(rows, wrap);
+  LM_CHECK(ensure(ctx, ctx->d_in, (rows == 0 ? 1 : rows + wrap) * 32));
+  uint8_t* d = (uint8_t*)ctx->d_in.p;
+  if (rows == 0) {
+    // DenseMatrix::resize default-fills new rows (dense.rs) and the loop at
+    // seq.rs:373-378 then copies defaults: every wrap row is the default symbol
+    std::vector<uint8_t> fill(32, pad_symbol(alphabet));
+    for (size_t i = 0; i < wrap; ++i) std::memcpy(data + i * stride, fill.data(), 32);
+    return LM_OK;
+  }
+  LM_TRY(cudaMemcpy2DAsync(d, 32, data, stride, 32, base, cudaMemcpyHostToDevice, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_wrap(d, rows, rows, rows + wrap, alphabet, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  LM_TRY(cudaMemcpy2DAsync(data + rows * stride, stride, d + rows * 32, 32, 32, wrap,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+static int score_rows_host(lm_ctx* ctx, int alphabet, bool is_u8, const void* pssm, size_t m,
+                           size_t pssm_stride, const uint8_t* seq, size_t rows, size_t wrap,
+                           size_t seq_stride, size_t length, size_t row_begin, size_t row_end,
+                           void* out, size_t out_stride, size_t* out_rows) {
+  LM_CHECK(bind(ctx));
+  if (out_rows) *out_rows = 0;
+  if (!valid_alphabet(alphabet) || !pssm || !seq || seq_stride < 32 || out_stride < 32 ||
+      pssm_stride < (size_t)alphabet_k(alphabet))
+    return LM_ERR_INVALID_ARG;
+  int st = check_score_args(m, rows, wrap, length, row_begin, row_end);
+  if (st == LM_EMPTY) return LM_OK;  // scores.resize(0, 0)
+  if (st < 0) return st;
+  if (!out) return LM_ERR_INVALID_ARG;
+  LM_CHECK(limits_ok(alphabet, m));
+  const size_t n = row_end - row_begin;
+  const size_t slab = std::min(rows + wrap, row_end + m - 1) - row_begin;  // rows uploaded
+  const size_t esz = is_u8 ? 1 : 4;
+  LM_CHECK(ensure(ctx, ctx->d_in, slab * 32));
+  LM_CHECK(ensure(ctx, ctx->d_out, n * 32 * esz));
+  LM_CHECK(upload_table(ctx, alphabet, pssm, m, pssm_stride, is_u8));
+  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32, seq + row_begin * seq_stride, seq_stride, 32, slab,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  LM_CHECK(run_score(ctx, alphabet, is_u8, MODE_STORE, (const uint8_t*)ctx->d_in.p, slab, m, 0, n,
+                     ctx->d_out.p, 32, 0.f, 0, nullptr, 0));
+  LM_TRY(cudaMemcpy2DAsync(out, out_stride * esz, ctx->d_out.p, 32 * esz, 32 * esz, n,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  if (out_rows) *out_rows = n;
+  return LM_OK;
+}
+
+int lm_score_f32_rows(lm_ctx* ctx, int alphabet, const float* pssm, size_t m, size_t pssm_stride,
+                      const uint8_t* seq, size_t rows, size_t wrap, size_t seq_stride, size_t length,
+                      size_t row_begin, size_t row_end, float* out, size_t out_stride,
+                      size_t* out_rows) {
+  return score_rows_host(ctx, alphabet, false, pssm, m, pssm_stride, seq, rows, wrap, seq_stride,
+                         length, row_begin, row_end, out, out_stride, out_rows);
+}
+
+int lm_score_u8_rows(lm_ctx* ctx, int alphabet, const uint8_t* dm, size_t m, size_t dm_stride,
+                     const uint8_t* seq, size_t rows, size_t wrap, size_t seq_stride, size_t length,
+                     size_t row_begin, size_t row_end, uint8_t* out, size_t out_stride,
+                     size_t* out_rows) {
+  return score_rows_host(ctx, alphabet, true, dm, m, dm_stride, seq, rows, wrap, seq_stride, length,
+                         row_begin, row_end, out, out_stride, out_rows);
+}
+
+static int reduce_host(lm_ctx* ctx, const void* scores, bool is_u8, size_t rows, size_t stride,
+                       ColKeys* ck) {
+  LM_CHECK(bind(ctx));
+  if (!scores || stride < 32) return LM_ERR_INVALID_ARG;
+  if (rows >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  const size_t esz = is_u8 ? 1 : 4;
+  LM_CHECK(ensure(ctx, ctx->d_in, rows * 32 * esz));
+  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* small = (uint8_t*)ctx->d_small.p;
+  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_colmax(ctx->d_in.p, is_u8, rows, 32, (unsigned long long*)small,
+                       (uint32_t*)(small + 256), ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  return fetch_colkeys(ctx, ck);
+}
+
+static int argmax_host(lm_ctx* ctx, const void* scores, bool is_u8, size_t rows, size_t stride,
+                       int rule, lm_hit* best) {
+  if (!best) return LM_ERR_INVALID_ARG;
+  if (rows == 0) return LM_EMPTY;  // pli/mod.rs:136-138
+  ColKeys ck;
+  LM_CHECK(reduce_host(ctx, scores, is_u8, rows, stride, &ck));
+  lm_colwin cw[32];
+  decode_colwins(ck.keys, is_u8, cw);
+  return apply_rule(cw, bits_to_score(ck.first_cell, is_u8), rule, is_u8, rows, 0, best);
+}
+
+int lm_argmax_f32(lm_ctx* ctx, const float* scores, size_t rows, size_t stride, int rule, lm_hit* best) {
+  return argmax_host(ctx, scores, false, rows, stride, rule, best);
+}
+int lm_argmax_u8(lm_ctx* ctx, const uint8_t* scores, size_t rows, size_t stride, int rule, lm_hit* best) {
+  return argmax_host(ctx, scores, true, rows, stride, rule, best);
+}
+
+int lm_max_f32(lm_ctx* ctx, const float* scores, size_t rows, size_t stride, float* best) {
+  lm_hit h;
+  int s = argmax_host(ctx, scores, false, rows, stride, LM_RULE_GENERIC, &h);
+  if (s == LM_OK && best) *best = h.score;
+  return s;
+}
+int lm_max_u8(lm_ctx* ctx, const uint8_t* scores, size_t rows, size_t stride, uint8_t* best) {
+  lm_hit h;
+  int s = argmax_host(ctx, scores, true, rows, stride, LM_RULE_GENERIC, &h);
+  if (s == LM_OK && best) *best = (uint8_t)h.score;
+  return s;
+}
+
+static int fetch_hits(lm_ctx* ctx, lm_hit* hits, size_t cap, size_t* count) {
+  unsigned long long total = 0;
+  LM_TRY(cudaMemcpyAsync(&total, (uint8_t*)ctx->d_small.p + 264, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  size_t n = (size_t)std::min<unsigned long long>(total, cap);
+  if (n) {
+    LM_TRY(cudaMemcpyAsync(hits, ctx->d_hits.p, n * sizeof(lm_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    LM_TRY(cudaStreamSynchronize(ctx->stream));
+    sort_hits(hits, n);  // the reference's row-major order (pli/mod.rs:212-219)
+  }
+  if (count) *count = (size_t)total;
+  return total > cap ? LM_ERR_OVERFLOW : LM_OK;
+}
+
+static int threshold_host(lm_ctx* ctx, const void* scores, bool is_u8, size_t rows, size_t stride,
+                          uint32_t thr_bits, lm_hit* hits, size_t cap, size_t* count) {
+  LM_CHECK(bind(ctx));
+  if (count) *count = 0;
+  if (rows == 0) return LM_OK;
+  if (!scores || stride < 32 || (cap && !hits)) return LM_ERR_INVALID_ARG;
+  const size_t esz = is_u8 ? 1 : 4;
+  LM_CHECK(ensure(ctx, ctx->d_in, rows * 32 * esz));
+  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
+  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
+                           cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* small = (uint8_t*)ctx->d_small.p;
+  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+  timer_begin(ctx);
+  LM_TRY(launch_threshold(ctx->d_in.p, is_u8, rows, 32, thr_bits, (lm_hit*)ctx->d_hits.p, cap,
+                          (unsigned long long*)(small + 264), ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  return fetch_hits(ctx, hits, cap, count);
+}
+
+int lm_threshold_f32(lm_ctx* ctx, const float* scores, size_t rows, size_t stride, float t,
+                     lm_hit* hits, size_t cap, size_t* count) {
+  uint32_t bits;
+  std::memcpy(&bits, &t, 4);
+  return threshold_host(ctx, scores, false, rows, stride, bits, hits, cap, count);
+}
+int lm_threshold_u8(lm_ctx* ctx, const uint8_t* scores, size_t rows, size_t stride, uint8_t t,
+                    lm_hit* hits, size_t cap, size_t* count) {
+  return threshold_host(ctx, scores, true, rows, stride, t, hits, cap, count);
+}
+
+// ------------------------------------------------ device-resident sequences
+
+static int seq_from_flat(lm_ctx* ctx, int alphabet, const uint8_t* src, size_t n, bool from_ascii,
+                         bool lossy, size_t wrap, lm_seq** out, size_t* bad_index) {
+  LM_CHECK(bind(ctx));
+  if (!out || !valid_alphabet(alphabet) || (n && !src)) return LM_ERR_INVALID_ARG;
+  *out = nullptr;
+  const size_t rows = (n + 31) / 32;
+  if (rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  lm_seq* s = nullptr;
+  LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, n, &s));
+  int st = LM_OK;
+  do {
+    if ((st = ensure(ctx, ctx->d_in, std::max<size_t>(n, 1))) < 0) break;
+    unsigned long long* d_bad = (unsigned long long*)ctx->d_small.p;
+    cudaError_t e = cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { st = fail(ctx, e, "upload"); break; }
+    timer_begin(ctx);
+    // every allocated row gets its closed-form value, so growing `wrap` later is free
+    e = launch_stripe((const uint8_t*)ctx->d_in.p, from_ascii, n, rows, 0, s->alloc_rows, s->data, alphabet,
+                      d_bad, ctx->sm_count, ctx->stream);
+    timer_end(ctx);
+    ctx->launches += 1;
+    if (e != cudaSuccess) { st = fail(ctx, e, "stripe kernel"); break; }
+    unsigned long long bad = ~0ull;
+    e = cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { st = fail(ctx, e, "stripe sync"); break; }
+    if (from_ascii && !lossy && bad != ~0ull) {
+      if (bad_index) *bad_index = (size_t)bad;
+      st = LM_ERR_INVALID_SYMBOL;
+    }
+  } while (0);
+  if (st < 0) { lm_seq_free(ctx, s); return st; }
+  *out = s;
+  return LM_OK;
+}
+
+int lm_seq_from_ascii(lm_ctx* ctx, int alphabet, const uint8_t* ascii, size_t n, int lossy, size_t wrap,
+                      lm_seq** out, size_t* bad_index) {
+  return seq_from_flat(ctx, alphabet, ascii, n, true, lossy != 0, wrap, out, bad_index);
+}
+
+int lm_seq_from_symbols(lm_ctx* ctx, int alphabet, const uint8_t* sym, size_t n, size_t wrap, lm_seq** out) {
+  return seq_from_flat(ctx, alphabet, sym, n, false, true, wrap, out, nullptr);
+}
+
+int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t rows, size_t wrap,
+                        size_t stride, size_t length, lm_seq** out) {
+  LM_CHECK(bind(ctx));
+  if (!out || !valid_alphabet(alphabet) || ((rows + wrap) && !data) || stride < 32 || length > rows * 32)
+    return LM_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  lm_seq* s = nullptr;
+  LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, length, &s));
+  cudaError_t e = cudaSuccess;
+  if (rows + wrap)
+    e = cudaMemcpy2DAsync(s->data, 32, data, stride, 32, rows + wrap, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(s->data + (rows + wrap) * 32, pad_symbol(alphabet), SLACK_ROWS * 32, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { int st = fail(ctx, e, "upload striped"); lm_seq_free(ctx, s); return st; }
+  *out = s;
+  return LM_OK;
+}
+
+int lm_seq_from_device(lm_ctx* ctx, int alphabet, void* device_ptr, size_t rows, size_t wrap,
+                       size_t length, lm_seq** out) {
+  LM_CHECK(bind(ctx));
+  if (!out || !valid_alphabet(alphabet) || !device_ptr || ((uintptr_t)device_ptr & 15) || length > rows * 32)
+    return LM_ERR_INVALID_ARG;
+  if (rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  lm_seq* s = new (std::nothrow) lm_seq();
+  if (!s) return LM_ERR_OOM;
+  s->alphabet = alphabet;
+  s->device = ctx->device;
+  s->data = (uint8_t*)device_ptr;
+  s->owned = false;
+  s->rows = rows;
+  s->wrap = wrap;
+  s->length = length;
+  s->alloc_rows = rows + wrap;
+  *out = s;
+  return LM_OK;
+}
+
+int lm_seq_synthetic(lm_ctx* ctx, int alphabet, uint64_t seed, uint64_t total_length, uint64_t row_begin,
+                     uint64_t n_rows, size_t wrap, lm_seq** out) {
+  LM_CHECK(bind(ctx));
+  if (!out || !valid_alphabet(alphabet)) return LM_ERR_INVALID_ARG;
+  *out = nullptr;
+  const uint64_t rows_global = (total_length + 31) / 32;
+  if (row_begin + n_rows > rows_global) return LM_ERR_INVALID_ARG;
+  if (rows_global + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  lm_seq* s = nullptr;
+  LM_CHECK(seq_alloc(ctx, alphabet, n_rows, wrap, total_length, &s));
+  timer_begin(ctx);
+  cudaError_t e = launch_synth(s->data, s->alloc_rows, rows_global, row_begin, total_length, seed, alphabet,
+                               ctx->sm_count, ctx->stream);
+  timer_end(ctx);
+  ctx->launches += 1;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { int st = fail(ctx, e, "synth kernel"); lm_seq_free(ctx, s); return st; }
+  *out = s;
+  return LM_OK;
+}
+
+int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
+  LM_CHECK(bind(ctx));
+  if (!seq) return LM_ERR_INVALID_ARG;
+  if (wrap <= seq->wrap) return LM_OK;  // seq.rs:370: only grows
+  if (!seq->owned) return LM_ERR_UNSUPPORTED;
+  if (seq->rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
+  if (seq->rows + wrap + SLACK_ROWS > seq->alloc_rows) {
+    size_t new_alloc = seq->rows + wrap + SLACK_ROWS;
+    uint8_t* nd = nullptr;
+    LM_TRY(cudaMalloc((void**)&nd, new_alloc * 32));
+    cudaError_t e = cudaMemcpyAsync(nd, seq->data, (seq->rows + seq->wrap) * 32, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(nd + (seq->rows + seq->wrap) * 32, pad_symbol(seq->alphabet),
+                                              (new_alloc - seq->rows - seq->wrap) * 32, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(nd); return fail(ctx, e, "grow sequence"); }
+    cudaFree(seq->data);
+    seq->data = nd;
+    seq->alloc_rows = new_alloc;
+  }
+  if (seq->rows == 0) {
+    LM_TRY(cudaMemsetAsync(seq->data, pad_symbol(seq->alphabet), wrap * 32, ctx->stream));
+  } else {
+    timer_begin(ctx);
+    LM_TRY(launch_wrap(seq->data, seq->rows, seq->rows + seq->wrap, seq->rows + wrap, seq->alphabet, ctx->stream));
+    timer_end(ctx);
+    ctx->launches += 1;
+  }
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  seq->wrap = wrap;
+  return LM_OK;
+}
+
+int lm_seq_info(const lm_seq* seq, int* alphabet, size_t* rows, size_t* wrap, size_t* length) {
+  if (!seq) return LM_ERR_INVALID_ARG;
+  if (alphabet) *alphabet = seq->alphabet;
+  if (rows) *rows = seq->rows;
+  if (wrap) *wrap = seq->wrap;
+  if (length) *length = seq->length;
+  return LM_OK;
+}
+
+void* lm_seq_device_ptr(const lm_seq* seq) { return seq ? seq->data : nullptr; }
+
+int lm_seq_download(lm_ctx* ctx, const lm_seq* seq, uint8_t* dst, size_t dst_stride) {
+  LM_CHECK(bind(ctx));
+  if (!seq || dst_stride < 32) return LM_ERR_INVALID_ARG;
+  size_t n = seq->rows + seq->wrap;
+  if (n == 0) return LM_OK;
+  if (!dst) return LM_ERR_INVALID_ARG;
+  LM_TRY(cudaMemcpy2DAsync(dst, dst_stride, seq->data, 32, 32, n, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+void lm_seq_free(lm_ctx* ctx, lm_seq* seq) {
+  if (!seq) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (seq->owned && seq->data) cudaFree(seq->data);
+  delete seq;
+}
+
+static int seq_score(lm_ctx* ctx, const lm_seq* seq, bool is_u8, const void* pssm, size_t m, size_t stride,
+                     size_t row_begin, size_t row_end, void* out, size_t out_stride, int out_is_device,
+                     size_t* out_rows) {
+  LM_CHECK(bind(ctx));
+  if (out_rows) *out_rows = 0;
+  if (!seq || !pssm || out_stride < 32 || stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
+  if (st == LM_EMPTY) return LM_OK;
+  if (st < 0) return st;
+  if (!out) return LM_ERR_INVALID_ARG;
+  LM_CHECK(limits_ok(seq->alphabet, m));
+  const size_t n = row_end - row_begin;
+  const size_t esz = is_u8 ? 1 : 4;
+  LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, stride, is_u8));
+  void* d_out = out;
+  size_t d_stride = out_stride;
+  if (!out_is_device) {
+    LM_CHECK(ensure(ctx, ctx->d_out, n * 32 * esz));
+    d_out = ctx->d_out.p;
+    d_stride = 32;
+  }
+  LM_CHECK(run_score(ctx, seq->alphabet, is_u8, MODE_STORE, seq->data, seq->alloc_rows, m, row_begin, row_end,
+                     d_out, d_stride, 0.f, 0, nullptr, 0));
+  if (!out_is_device)
+    LM_TRY(cudaMemcpy2DAsync(out, out_stride * esz, d_out, 32 * esz, 32 * esz, n, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  if (out_rows) *out_rows = n;
+  return LM_OK;
+}
+
+int lm_seq_score_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
+                     size_t row_begin, size_t row_end, float* out, size_t out_stride, int out_is_device,
+                     size_t* out_rows) {
+  return seq_score(ctx, seq, false, pssm, m, pssm_stride, row_begin, row_end, out, out_stride, out_is_device, out_rows);
+}
+
+int lm_seq_score_u8(lm_ctx* ctx, const lm_seq* seq, const uint8_t* dm, size_t m, size_t dm_stride,
+                    size_t row_begin, size_t row_end, uint8_t* out, size_t out_stride, int out_is_device,
+                    size_t* out_rows) {
+  return seq_score(ctx, seq, true, dm, m, dm_stride, row_begin, row_end, out, out_stride, out_is_device, out_rows);
+}
+
+int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
+                            size_t row_begin, size_t row_end, int rule, lm_hit* best, lm_colwin* per_column,
+                            float* first_cell) {
+  LM_CHECK(bind(ctx));
+  if (!seq || !pssm || !best || pssm_stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  if (per_column) std::memset(per_column, 0, 32 * sizeof(lm_colwin));
+  int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
+  if (st != LM_OK) return st;
+  LM_CHECK(limits_ok(seq->alphabet, m));
+  LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
+  LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin, row_end,
+                     nullptr, 0, 0.f, 0, nullptr, 0));
+  ColKeys ck;
+  LM_CHECK(fetch_colkeys(ctx, &ck));
+  lm_colwin cw[32];
+  decode_colwins(ck.keys, false, cw);
+  if (per_column) std::memcpy(per_column, cw, sizeof(cw));
+  if (first_cell) *first_cell = bits_to_score(ck.first_cell, false);
+  return apply_rule(cw, bits_to_score(ck.first_cell, false), rule, false, row_end - row_begin, 0, best);
+}
+
+int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
+                               size_t row_begin, size_t row_end, float t, lm_hit* hits, size_t cap, size_t* count) {
+  LM_CHECK(bind(ctx));
+  if (count) *count = 0;
+  if (!seq || !pssm || (cap && !hits) || pssm_stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
+  if (st == LM_EMPTY) return LM_OK;
+  if (st < 0) return st;
+  LM_CHECK(limits_ok(seq->alphabet, m));
+  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
+  LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
+  LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_THRESHOLD, seq->data, seq->alloc_rows, m, row_begin, row_end,
+                     nullptr, 0, t, 0, (lm_hit*)ctx->d_hits.p, cap));
+  return fetch_hits(ctx, hits, cap, count);
+}
+
+int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                  const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int rule,
+                                  lm_hit* best) {
+  LM_CHECK(bind(ctx));
+  if (!seq || !pssms || !widths || !offsets || !best || pssm_stride < (size_t)alphabet_k(seq->alphabet))
+    return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  if (n_motifs == 0) return LM_OK;
+  if (n_motifs > 65536) return LM_ERR_UNSUPPORTED;
+  const int alphabet = seq->alphabet;
+  const int kp = table_kp(alphabet);
+  size_t max_m = 0, total_words = 0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    if (widths[q] == 0) return LM_ERR_INVALID_ARG;
+    max_m = std::max<size_t>(max_m, widths[q]);
+    total_words += (size_t)table_mpad(widths[q]) * kp;
+  }
+  int st = check_score_args(max_m, seq->rows, seq->wrap, seq->length, 0, seq->rows);
+  if (st < 0) return st;
+  LM_CHECK(limits_ok(alphabet, max_m));
+  // host staging: [tables | table_off u64 | m_pads i32]
+  const size_t tab_bytes = total_words * 4;
+  const size_t off_bytes = n_motifs * 8, mp_bytes = n_motifs * 4;
+  const size_t stage_bytes = tab_bytes + off_bytes + mp_bytes + 64;
+  LM_CHECK(ensure_pinned(ctx, stage_bytes));
+  LM_CHECK(ensure(ctx, ctx->d_table, stage_bytes));
+  uint8_t* h = (uint8_t*)ctx->h_pin;
+  uint32_t* h_tab = (uint32_t*)h;
+  size_t off_at = (tab_bytes + 15) & ~(size_t)15;
+  uint64_t* h_off = (uint64_t*)(h + off_at);
+  int* h_mp = (int*)(h + off_at + off_bytes);
+  size_t w = 0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    h_off[q] = w;
+    h_mp[q] = table_mpad(widths[q]);
+    build_table_f32(alphabet, pssms + offsets[q], widths[q], pssm_stride, h_tab + w);
+    w += (size_t)h_mp[q] * kp;
+  }
+  LM_TRY(cudaMemcpyAsync(ctx->d_table.p, h, off_at + off_bytes + mp_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t key_bytes = n_motifs * 32 * 8, fc_bytes = n_motifs * 4;
+  LM_CHECK(ensure(ctx, ctx->d_out, key_bytes + fc_bytes));
+  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, key_bytes + fc_bytes, ctx->stream));
+  // motifs shorter than the sequence's length are all scorable; a motif longer
+  // than the sequence yields LM_EMPTY semantics (position = 0, valid = 0)
+  ScoreArgs a;
+  a.seq = seq->data;
+  a.avail_rows = seq->alloc_rows;
+  a.row_begin = 0;
+  a.row_end = seq->rows;
+  a.pad_sym = pad_symbol(alphabet);
+  uint8_t* d = (uint8_t*)ctx->d_table.p;
+  a.tables = (const uint32_t*)d;
+  a.table_off = (const uint64_t*)(d + off_at);
+  a.m_pads = (const int*)(d + off_at + off_bytes);
+  a.m_pad = table_mpad(max_m);
+  a.n_motifs = (int)n_motifs;
+  a.colkeys = (unsigned long long*)ctx->d_out.p;
+  a.first_cell = (uint32_t*)((uint8_t*)ctx->d_out.p + key_bytes);
+  timer_begin(ctx);
+  LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, ctx->sm_count, ctx->stream));
+  timer_end(ctx);
+  ctx->launches += 1;
+  std::vector<unsigned long long> keys(n_motifs * 32);
+  std::vector<uint32_t> fc(n_motifs);
+  LM_TRY(cudaMemcpyAsync(keys.data(), a.colkeys, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(fc.data(), a.first_cell, fc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  for (size_t q = 0; q < n_motifs; ++q) {
+    lm_colwin cw[32];
+    decode_colwins(&keys[q * 32], false, cw);
+    std::memset(&best[q], 0, sizeof(lm_hit));
+    if (seq->length < widths[q]) continue;
+    apply_rule(cw, bits_to_score(fc[q], false), rule, false, seq->rows, 0, &best[q]);
+  }
+  return LM_OK;
+}
+
+int lm_argmax_merge(const lm_colwin* parts, size_t n_parts, const uint64_t* row_offsets, float first_cell,
+                    uint64_t total_rows, int rule, lm_hit* best) {
+  if (!parts || !row_offsets || !best || n_parts == 0) return LM_ERR_INVALID_ARG;
+  lm_colwin cw[32];
+  for (int c = 0; c < 32; ++c) {
+    cw[c].valid = 0; cw[c].row = 0; cw[c].score = 0.f;
+    for (size_t p = 0; p < n_parts; ++p) {
+      const lm_colwin& x = parts[p * 32 + c];
+      if (!x.valid) continue;
+      // later slabs hold larger rows: '>=' keeps the last row on ties
+      if (!cw[c].valid || x.score >= cw[c].score) {
+        cw[c].valid = 1;
+        cw[c].score = x.score;
+        cw[c].row = row_offsets[p] + x.row;
+      }
+    }
+  }
+  return apply_rule(cw, first_cell, rule, false, total_rows, row_offsets[0], best);
+}
+
+}  // extern "C"

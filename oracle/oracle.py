@@ -187,7 +187,7 @@ def stripe(alphabet, sym, c=LANES, wrap=0):
     rows = lib().lmo_stripe_rows(sym.size, c)
     pad = default_symbol(alphabet)
     data = aligned_empty((rows + wrap, c), np.uint8)
-    data[rows:, :] = 255  # poison: configure_wrap must overwrite
+    data[rows:, :] = pad  # DenseMatrix::resize default-fills new rows (dense.rs)
     lib().lmo_stripe(_p(sym, _u8p), sym.size, c, pad, _p(data, _u8p), c)
     if wrap:
         lib().lmo_configure_wrap(_p(data, _u8p), rows, c, c, wrap, pad)

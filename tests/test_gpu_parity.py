@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs -- bit-exact for symbols, u8 scores, indices AND f32
+scores (the kernels keep the reference's sequential summation order)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402  (checker only)
+
+LETTERS = np.frombuffer(b"ACTGN", dtype=np.uint8)
+AA = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYX", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def lm():
+    import lightmotif_b200 as lm
+    return lm
+
+
+@pytest.fixture(scope="module")
+def dna(lm):
+    p = lm.Pipeline.cuda(lm.DNA)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def prot(lm):
+    p = lm.Pipeline.cuda(lm.PROTEIN)
+    yield p
+    p.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def random_pssm(rng, m, k, neg_inf_cells=0):
+    p = rng.normal(0, 2, size=(m, k)).astype(np.float32)
+    p[:, k - 1] = -np.inf
+    for _ in range(neg_inf_cells):
+        p[rng.integers(0, m), rng.integers(0, k - 1)] = -np.inf
+    return p
+
+
+# ------------------------------------------------------------------ encode
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 64, 1000, 65537])
+def test_encode_matches_oracle(dna, prot, n):
+    rng = np.random.default_rng(n)
+    a = LETTERS[rng.integers(0, 5, n)]
+    assert np.array_equal(dna.encode(a), O.encode(O.DNA, a))
+    b = AA[rng.integers(0, 21, n)]
+    assert np.array_equal(prot.encode(b), O.encode(O.PROTEIN, b))
+
+
+def test_encode_kat_and_errors(lm, dna, kat):
+    e = kat["encode"]
+    assert dna.encode(e["sequence"]).tolist() == [e["codes"][c] for c in e["expected_letters"]]
+    with pytest.raises(lm.InvalidSymbol) as ei:
+        dna.encode(e["unknowns"])
+    assert ei.value.ch == "." and ei.value.index == e["unknowns"].index(".")
+    assert np.array_equal(dna.encode_lossy(e["unknowns"]), O.encode_lossy(O.DNA, e["unknowns"]))
+    # first invalid byte wins, wherever it is; lower case is invalid
+    rng = np.random.default_rng(7)
+    a = LETTERS[rng.integers(0, 4, 100000)].copy()
+    a[[77777, 99999, 12345]] = ord("x")
+    with pytest.raises(lm.InvalidSymbol) as ei:
+        dna.encode(a)
+    assert ei.value.index == 12345 and ei.value.ch == "x"
+    with pytest.raises(lm.InvalidSymbol):
+        dna.encode("acgt")
+    # unaligned host views
+    buf = LETTERS[rng.integers(0, 5, 4099)]
+    assert np.array_equal(dna.encode(buf[3:]), O.encode(O.DNA, buf[3:]))
+
+
+# ------------------------------------------------------------ stripe / wrap
+
+@pytest.mark.parametrize("n,wrap", [(0, 0), (0, 3), (1, 0), (5, 2), (31, 4), (32, 1), (33, 14), (64, 14),
+                                    (40, 9), (1031, 40), (100003, 29), (4096, 0)])
+def test_stripe_wrap_matches_oracle(dna, n, wrap):
+    rng = np.random.default_rng(n + wrap)
+    sym = rng.integers(0, 5, n).astype(np.uint8)
+    want = O.stripe(O.DNA, sym, 32, wrap)
+    got = dna.stripe(sym, wrap)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    seq = dna.sequence_from_symbols(sym, wrap)
+    assert (seq.rows, seq.wrap, seq.length) == (want.shape[0] - wrap, wrap, n)
+    assert np.array_equal(seq.download(), want)
+    ascii_ = LETTERS[sym]
+    seq2 = dna.sequence_from_ascii(ascii_, wrap)
+    assert np.array_equal(seq2.download(), want)
+    seq.configure_wrap(wrap + 7)  # grow on the device
+    assert np.array_equal(seq.download(), O.stripe(O.DNA, sym, 32, wrap + 7))
+    up = dna.sequence_from_striped(want, n, wrap)
+    up.configure_wrap(wrap + 5)
+    assert np.array_equal(up.download(), O.stripe(O.DNA, sym, 32, wrap + 5))
+
+
+def test_stripe_kat(dna, kat):
+    s = kat["stripe"]
+    for seq in (s["s2"], s["s1_unit"] * s["s1_repeats"] + s["s1_tail"]):
+        enc = dna.encode(seq)
+        m = dna.stripe(enc)
+        rows = m.shape[0]
+        idx = np.arange(len(seq))
+        assert np.array_equal(m[idx % rows, idx // rows], enc)
+        idx = np.arange(len(seq), rows * 32)
+        assert np.all(m[idx % rows, idx // rows] == 4)
+
+
+def test_sequence_from_ascii_errors(lm, dna):
+    with pytest.raises(lm.InvalidSymbol) as ei:
+        dna.sequence_from_ascii("ACGT" * 100 + "Z" + "ACGT" * 50, 3)
+    assert ei.value.index == 400
+    seq = dna.sequence_from_ascii("ACGT" * 100 + "Z" + "ACGT" * 50, 3, lossy=True)
+    want = O.stripe(O.DNA, O.encode_lossy(O.DNA, "ACGT" * 100 + "Z" + "ACGT" * 50), 32, 3)
+    assert np.array_equal(seq.download(), want)
+
+
+# ------------------------------------------------------------------- score
+
+def test_score_kat(dna, kat):
+    """lightmotif/tests/dna.rs: test_score, test_score_rows, test_argmax, test_threshold."""
+    d = kat["dna"]
+    pssm = O.pssm_from_sequences(O.DNA, d["patterns"], d["pseudocount"])
+    enc = dna.encode(d["sequence"])
+    striped = dna.stripe(enc, wrap=len(pssm) - 1)
+    n = len(d["sequence"])
+    sc = dna.score_rows(pssm, striped, n, len(pssm) - 1)
+    want = O.score_f32(pssm, O.stripe(O.DNA, enc, 32, 14), n)
+    assert np.array_equal(bits(sc), bits(want))
+    u = O.unstripe(sc, n + 1 - len(pssm))
+    exp = np.array(d["expected"], dtype=np.float32)
+    assert np.abs(u - exp).max() < d["tolerance"]
+    assert u[0] == exp[0] and u[1] == exp[1]
+    s02 = dna.score_rows(pssm, striped, n, 14, rows=(0, 2))
+    assert s02.shape[0] == 2 and s02[0, 0] == exp[0] and s02[1, 0] == exp[1]
+    s12 = dna.score_rows(pssm, striped, n, 14, rows=(1, 2))
+    assert s12.shape[0] == 1 and s12[0, 0] == exp[1]
+    assert dna.score_rows(pssm, striped, n, 14, rows=(1, 1)).shape[0] == 0  # pli/mod.rs:603-623
+    for rule in (0, 1, 2):
+        mc = dna.argmax(sc, rule)
+        assert mc.col * sc.shape[0] + mc.row == d["argmax"]
+    for t, hits in d["threshold"].items():
+        got = dna.threshold(sc, float(t))
+        assert sorted(h.col * sc.shape[0] + h.row for h in got) == hits
+        ro, co = O.threshold(sc, float(t))
+        assert [(h.row, h.col) for h in got] == list(zip(ro.tolist(), co.tolist()))
+    assert dna.threshold(sc, 10.0) == []
+    seq = dna.sequence_from_symbols(enc, 14)
+    best = seq.score_argmax(pssm)
+    assert best["position"] == d["argmax"] and np.float32(best["score"]) == u[18]
+    hits = seq.score_threshold(pssm, -15.0)
+    assert sorted(h["position"] for h in hits) == d["threshold"]["-15.0"]
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 7, 8, 15, 16, 20, 21, 33, 64])
+@pytest.mark.parametrize("n", [50, 4099])
+def test_score_random_dna(dna, m, n):
+    rng = np.random.default_rng(1000 * m + n)
+    pssm = random_pssm(rng, m, 5, neg_inf_cells=m // 8)
+    sym = rng.choice(5, size=n, p=[0.24, 0.25, 0.25, 0.24, 0.02]).astype(np.uint8)
+    st = O.stripe(O.DNA, sym, 32, m - 1)
+    want = O.score_f32(pssm, st, n)
+    seq = dna.sequence_from_symbols(sym, m - 1)
+    if n < m:
+        assert seq.score(pssm).shape[0] == 0
+        return
+    got = seq.score(pssm)
+    assert np.array_equal(bits(got), bits(want))
+    rows = st.shape[0] - (m - 1)
+    lo, hi = rows // 3, max(rows // 3 + 1, 2 * rows // 3)
+    assert np.array_equal(bits(seq.score(pssm, rows=(lo, hi))), bits(want[lo:hi]))
+    assert np.array_equal(bits(dna.score_rows(pssm, st, n, m - 1)), bits(want))
+    for rule in (0, 1, 2):
+        r, c = O.argmax(want, rule)
+        best = seq.score_argmax(pssm, rule=rule)
+        assert (best["row"], best["col"]) == (r, c), rule
+        assert bits(np.float32(best["score"])) == bits(want[r, c])
+        mc = dna.argmax(want, rule)
+        assert (mc.row, mc.col) == (r, c)
+    finite = want[np.isfinite(want)]
+    t = float(np.quantile(finite, 0.9)) if finite.size else 0.0
+    ro, co = O.threshold(want, t)
+    hits = seq.score_threshold(pssm, t)
+    assert [(h["row"], h["col"]) for h in hits] == list(zip(ro.tolist(), co.tolist()))
+    assert np.array_equal(bits(np.array([h["score"] for h in hits], np.float32)), bits(want[ro, co]))
+    assert dna.max(want) == O.max_(want)
+
+
+def test_wrap_and_length_errors(lm, dna):
+    rng = np.random.default_rng(3)
+    sym = rng.integers(0, 4, 300).astype(np.uint8)
+    pssm = random_pssm(rng, 10, 5)
+    seq = dna.sequence_from_symbols(sym, 5)
+    with pytest.raises(lm.LightmotifError) as ei:
+        seq.score(pssm)
+    assert ei.value.status == lm.capi.ERR_WRAP
+    short = dna.sequence_from_symbols(sym[:6], 9)
+    assert short.score(pssm).shape[0] == 0 and short.score_argmax(pssm) is None
+    assert short.score_threshold(pssm, -100.0) == []
+    assert dna.argmax(np.zeros((0, 32), np.float32)) is None
+
+
+def test_score_ecoli(dna, kat, ecoli_codes, ecoli_kat):
+    """tests/argmax.rs (first tenth: tie 391677 / 401649) and the full genome."""
+    k = kat["ecoli_tenth"]
+    pssm = O.pssm_from_sequences(O.DNA, k["patterns"], 0.1)
+    enc = ecoli_codes[: k["n"]]
+    seq = dna.sequence_from_symbols(enc, 14)
+    want = O.score_f32(pssm, O.stripe(O.DNA, enc, 32, 14), k["n"])
+    assert np.array_equal(bits(seq.score(pssm)), bits(want))
+    for rule in (0, 1, 2):
+        best = seq.score_argmax(pssm, rule=rule)
+        assert best["position"] == k["argmax_pipeline"]
+        assert np.float32(best["score"]) == want.max()
+    n = ecoli_codes.size
+    full = dna.sequence_from_symbols(ecoli_codes, 14)
+    wantf = O.score_f32(pssm, O.stripe(O.DNA, ecoli_codes, 32, 14), n)
+    assert np.array_equal(bits(full.score(pssm)), bits(wantf))
+    best = full.score_argmax(pssm)
+    assert best["position"] == ecoli_kat["full_genome_argmax_last"]
+    assert best["score"] == ecoli_kat["full_genome_max"]
+    hits = full.score_threshold(pssm, 10.0)
+    assert len(hits) == ecoli_kat["count_ge_10"]
+    ro, co = O.threshold(wantf, 10.0)
+    assert [(h["row"], h["col"]) for h in hits] == list(zip(ro.tolist(), co.tolist()))
+
+
+def test_score_u8(dna, kat, ecoli_codes):
+    d = kat["dna"]
+    pssm = O.pssm_from_sequences(O.DNA, d["patterns"], d["pseudocount"])
+    dm = O.Discrete(O.DNA, pssm)
+    enc = ecoli_codes[:200003]
+    st = O.stripe(O.DNA, enc, 32, 14)
+    want = O.score_u8(dm.data, st, enc.size)
+    seq = dna.sequence_from_symbols(enc, 14)
+    got = seq.score(dm.data)
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    assert np.array_equal(dna.score_rows(dm.data, st, enc.size, 14), want)
+    # saturation: a matrix whose sums exceed 255
+    big = np.full((20, 5), 40, np.uint8)
+    seq.configure_wrap(19)
+    st19 = O.stripe(O.DNA, enc, 32, 19)
+    assert np.array_equal(seq.score(big), O.score_u8(big, st19, enc.size))
+    assert int(seq.score(big).max()) == 255
+    for rule in (0, 1):
+        r, c = O.argmax(want, rule)
+        mc = dna.argmax(want, rule)
+        assert (mc.row, mc.col) == (r, c)
+    assert dna.max(want) == O.max_(want)
+    t = int(want.max()) - 3
+    ro, co = O.threshold(want, t)
+    assert [(h.row, h.col) for h in dna.threshold(want, t)] == list(zip(ro.tolist(), co.tolist()))
+
+
+def test_score_protein(prot, kat, abyb1):
+    p = kat["protein"]
+    pssm = O.pssm_from_sequences(O.PROTEIN, p["patterns"], p["pseudocount"])
+    for m in (15, 23):
+        ps = pssm[:m]
+        enc = prot.encode(abyb1)
+        assert np.array_equal(enc, O.encode(O.PROTEIN, abyb1))
+        st = O.stripe(O.PROTEIN, enc, 32, m - 1)
+        want = O.score_f32(ps, st, enc.size)
+        seq = prot.sequence_from_ascii(abyb1, m - 1)
+        assert np.array_equal(seq.download(), st)
+        assert np.array_equal(bits(seq.score(ps)), bits(want))
+        r, c = O.argmax(want, O.RULE_AVX2)
+        best = seq.score_argmax(ps)
+        assert (best["row"], best["col"]) == (r, c)
+    n = 300007
+    sym = O.synth_protein(n)
+    sym[::1000] = 20  # some X
+    ps = pssm[:15]
+    want = O.score_f32(ps, O.stripe(O.PROTEIN, sym, 32, 14), n)
+    seq = prot.sequence_from_symbols(sym, 14)
+    assert np.array_equal(bits(seq.score(ps)), bits(want))
+    for rule in (0, 1, 2):
+        r, c = O.argmax(want, rule)
+        best = seq.score_argmax(ps, rule=rule)
+        assert (best["row"], best["col"]) == (r, c)
+
+
+def test_synthetic_matches_oracle(dna, prot):
+    n = 100003
+    for pli, alpha, gen in ((dna, O.DNA, O.synth_dna), (prot, O.PROTEIN, O.synth_protein)):
+        want = O.stripe(alpha, gen(n), 32, 19)
+        seq = pli.sequence_synthetic(n, 19)
+        assert np.array_equal(seq.download(), want)
+        rows = want.shape[0] - 19
+        lo, cnt = 1000, 777  # a row slab generated in place, halo taken from the following rows
+        slab = pli.sequence_synthetic(n, 19, row_begin=lo, n_rows=cnt)
+        assert np.array_equal(slab.download(), want[lo:lo + cnt + 19])
+        assert rows > lo + cnt
+
+
+def test_batch_argmax(dna, jaspar):
+    n = 200000
+    sym = O.synth_dna(n)
+    motifs = jaspar["motifs"][:48] + [jaspar["rest"]]
+    pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in motifs]
+    maxw = max(len(p) for p in pssms)
+    seq = dna.sequence_from_symbols(sym, maxw - 1)
+    got = seq.score_argmax_batch(pssms)
+    st = O.stripe(O.DNA, sym, 32, maxw - 1)
+    for p, g in zip(pssms, got):
+        want = O.score_f32(p, st, n, wrap=maxw - 1)
+        r, c = O.argmax(want, O.RULE_AVX2)
+        assert (g["row"], g["col"]) == (r, c)
+        assert bits(np.float32(g["score"])) == bits(want[r, c])
+        single = seq.score_argmax(p)
+        assert (single["row"], single["col"]) == (r, c)
+
+
+def test_sharded_merge_equals_single_call(lm, dna, jaspar):
+    """Row slabs scored independently + lm_argmax_merge == one call (the
+    multi-GPU reduction, exercised on one device)."""
+    n = 1000003
+    pssm = O.pssm_from_counts(O.DNA, jaspar["rest"], 0.1)
+    m = len(pssm)
+    whole = dna.sequence_synthetic(n, m - 1)
+    rows = whole.rows
+    for rule in (0, 1, 2):
+        ref = whole.score_argmax(pssm, rule=rule)
+        cuts = [0, rows // 5, rows // 2, rows - 7, rows]
+        parts, first = [], None
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            slab = dna.sequence_synthetic(n, m - 1, row_begin=lo, n_rows=hi - lo)
+            res = slab.score_argmax(pssm, rule=rule, with_columns=True)
+            parts.append(res["columns"])
+            if first is None:
+                first = res["first_cell"]
+        merged = lm.argmax_merge(parts, cuts, first, rows, rule)
+        assert (merged["row"], merged["col"], merged["position"]) == (ref["row"], ref["col"], ref["position"])
+        assert merged["score"] == ref["score"]
+    st = O.stripe(O.DNA, O.synth_dna(n), 32, m - 1)
+    want = O.score_f32(pssm, st, n)
+    r, c = O.argmax(want, O.RULE_AVX2)
+    ref = whole.score_argmax(pssm)
+    assert (ref["row"], ref["col"]) == (r, c)
+
+
+def test_kernels_actually_launched(dna):
+    before = dna.kernel_launches
+    dna.encode("ACGT")
+    assert dna.kernel_launches == before + 1
