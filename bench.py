@@ -162,6 +162,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import lightmotif_b200 as lm
+    from lightmotif_b200 import dist as lmdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,13 +191,7 @@ def run_ours(args):
         res = seq.score_argmax(pssm, rule=lm.RULE_AVX2, with_columns=True)
         kms = pli.last_kernel_ms
         if world > 1:  # global argmax: all-gather of per-column winners over NVLink, then merge
-            cols = torch.tensor([[r, s, v] for (r, s, v) in res["columns"]] + [[r0, res["first_cell"], 1.0]],
-                                dtype=torch.float64, device=dev)
-            out = [torch.empty_like(cols) for _ in range(world)]
-            dist.all_gather(out, cols)
-            parts = [[(int(x[0]), float(x[1]), int(x[2])) for x in o[:32].tolist()] for o in out]
-            offs = [int(o[32][0].item()) for o in out] + [rows_global]
-            res = lm.argmax_merge(parts, offs, float(out[0][32][1].item()), rows_global, lm.RULE_AVX2)
+            res = lmdist.allgather_merge(res, r0, rows_global, lm.RULE_AVX2, device=dev)
         return res, kms
 
     def sync_all():

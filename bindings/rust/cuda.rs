@@ -1,0 +1,245 @@
+//! `lightmotif::pli::platform::cuda` -- the back-end a lightmotif maintainer
+//! adds to bind liblightmotif_b200.so.  SOURCE ONLY: there is no Rust
+//! toolchain in the build image, so this file has not been compiled; the C ABI
+//! it binds is exercised from C++ (tests/cpp) and Python (tests/test_gpu_*.py).
+//!
+//! Drop next to `avx2.rs` (lightmotif/src/pli/platform/), add `pub mod cuda;`
+//! + `pub use cuda::Cuda;` to platform/mod.rs, and the impls below to
+//! pli/mod.rs (same shape as the Avx2 block, pli/mod.rs:399-493).
+
+use std::ops::Range;
+use std::os::raw::{c_int, c_void};
+
+use crate::abc::{Alphabet, Dna, Symbol};
+use crate::dense::{DenseMatrix, MatrixCoordinates};
+use crate::err::{InvalidSymbol, UnsupportedBackend};
+use crate::num::{Unsigned, U32};
+use crate::pli::{Encode, Maximum, Pipeline, Score, Stripe, Threshold};
+use crate::scores::StripedScores;
+use crate::seq::StripedSequence;
+
+use super::Backend;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct LmHit {
+    pub row: u64,
+    pub position: u64,
+    pub col: u32,
+    pub score: f32,
+}
+
+#[allow(non_camel_case_types)]
+type lm_ctx = c_void;
+
+#[link(name = "lightmotif_b200")]
+extern "C" {
+    fn lm_ctx_create(device: c_int, out: *mut *mut lm_ctx) -> c_int;
+    fn lm_ctx_destroy(ctx: *mut lm_ctx);
+    fn lm_encode(ctx: *mut lm_ctx, alphabet: c_int, ascii: *const u8, n: usize, dst: *mut u8,
+                 bad_index: *mut usize) -> c_int;
+    fn lm_stripe(ctx: *mut lm_ctx, alphabet: c_int, sym: *const u8, n: usize, dst: *mut u8,
+                 dst_stride: usize) -> c_int;
+    fn lm_score_f32_rows(ctx: *mut lm_ctx, alphabet: c_int, pssm: *const f32, m: usize,
+                         pssm_stride: usize, seq: *const u8, rows: usize, wrap: usize,
+                         seq_stride: usize, length: usize, row_begin: usize, row_end: usize,
+                         out: *mut f32, out_stride: usize, out_rows: *mut usize) -> c_int;
+    fn lm_score_u8_rows(ctx: *mut lm_ctx, alphabet: c_int, dm: *const u8, m: usize,
+                        dm_stride: usize, seq: *const u8, rows: usize, wrap: usize,
+                        seq_stride: usize, length: usize, row_begin: usize, row_end: usize,
+                        out: *mut u8, out_stride: usize, out_rows: *mut usize) -> c_int;
+    fn lm_argmax_f32(ctx: *mut lm_ctx, scores: *const f32, rows: usize, stride: usize,
+                     rule: c_int, best: *mut LmHit) -> c_int;
+    fn lm_max_f32(ctx: *mut lm_ctx, scores: *const f32, rows: usize, stride: usize,
+                  best: *mut f32) -> c_int;
+    fn lm_threshold_f32(ctx: *mut lm_ctx, scores: *const f32, rows: usize, stride: usize, t: f32,
+                        hits: *mut LmHit, cap: usize, count: *mut usize) -> c_int;
+}
+
+const LM_OK: c_int = 0;
+const LM_EMPTY: c_int = 1;
+const LM_ERR_INVALID_SYMBOL: c_int = -2;
+const LM_ERR_WRAP: c_int = -3;
+const LM_ERR_OVERFLOW: c_int = -7;
+const LM_RULE_AVX2: c_int = 1;
+
+/// A marker type for the CUDA (B200, sm_100a) implementation of the pipeline.
+/// Unlike the SIMD markers it carries a per-thread context handle.
+#[derive(Debug)]
+pub struct Cuda {
+    ctx: *mut lm_ctx,
+}
+
+unsafe impl Send for Cuda {}
+
+impl Backend for Cuda {
+    type Lanes = U32; // the device reads DenseMatrix<_, U32> rows as-is (one warp per row)
+}
+
+impl Drop for Cuda {
+    fn drop(&mut self) {
+        unsafe { lm_ctx_destroy(self.ctx) }
+    }
+}
+
+/// Alphabet tag passed over the ABI (LM_DNA = 0, LM_PROTEIN = 1).
+fn alphabet_tag<A: Alphabet>() -> c_int {
+    if A::K::USIZE == 5 { 0 } else { 1 }
+}
+
+impl<A: Alphabet> Pipeline<A, Cuda> {
+    /// Attempt to create a new CUDA-accelerated pipeline (cf. `Pipeline::avx2`,
+    /// pli/mod.rs:401-407).
+    pub fn cuda() -> Result<Self, UnsupportedBackend> {
+        let mut ctx = std::ptr::null_mut();
+        match unsafe { lm_ctx_create(0, &mut ctx) } {
+            LM_OK => Ok(Self::with_backend(Cuda { ctx })),
+            _ => Err(UnsupportedBackend),
+        }
+    }
+}
+
+impl<A: Alphabet> Encode<A> for Pipeline<A, Cuda> {
+    fn encode_into<S: AsRef<[u8]>>(&self, seq: S, dst: &mut [A::Symbol]) -> Result<(), InvalidSymbol> {
+        let s = seq.as_ref();
+        assert_eq!(s.len(), dst.len());
+        let mut bad = 0usize;
+        let st = unsafe {
+            lm_encode(self.backend().ctx, alphabet_tag::<A>(), s.as_ptr(), s.len(),
+                      dst.as_mut_ptr() as *mut u8, &mut bad)
+        };
+        match st {
+            LM_OK => Ok(()),
+            LM_ERR_INVALID_SYMBOL => Err(InvalidSymbol(s[bad] as char)),
+            e => panic!("lightmotif_b200: lm_encode failed with status {}", e),
+        }
+    }
+}
+
+impl<A: Alphabet> Stripe<A, U32> for Pipeline<A, Cuda> {
+    fn stripe_into<S: AsRef<[A::Symbol]>>(&self, seq: S, striped: &mut StripedSequence<A, U32>) {
+        let s = seq.as_ref();
+        let rows = s.len().div_ceil(32);
+        let mut data = std::mem::take(striped).into_matrix();
+        data.reserve(rows + crate::seq::DEFAULT_EXTRA_ROWS);
+        data.resize(rows);
+        if rows > 0 {
+            let st = unsafe {
+                lm_stripe(self.backend().ctx, alphabet_tag::<A>(), s.as_ptr() as *const u8, s.len(),
+                          data[0].as_mut_ptr() as *mut u8, data.stride())
+            };
+            assert_eq!(st, LM_OK, "lightmotif_b200: lm_stripe failed");
+        }
+        *striped = StripedSequence::new(data, s.len()).unwrap();
+    }
+}
+
+impl<A: Alphabet> Score<f32, A, U32> for Pipeline<A, Cuda> {
+    fn score_rows_into<S, M>(&self, pssm: M, seq: S, rows: Range<usize>, scores: &mut StripedScores<f32, U32>)
+    where
+        S: AsRef<StripedSequence<A, U32>>,
+        M: AsRef<DenseMatrix<f32, A::K>>,
+    {
+        let seq = seq.as_ref();
+        let pssm = pssm.as_ref();
+        if seq.len() < pssm.rows() || rows.is_empty() {
+            scores.resize(0, 0);
+            return;
+        }
+        // the Rust side keeps owning (and resizing) the output, avx2.rs:844
+        scores.resize(rows.len(), (seq.len() + 1).saturating_sub(pssm.rows()));
+        let m = seq.matrix();
+        let mut out_rows = 0usize;
+        let st = unsafe {
+            lm_score_f32_rows(
+                self.backend().ctx, alphabet_tag::<A>(), pssm[0].as_ptr(), pssm.rows(), pssm.stride(),
+                m[0].as_ptr() as *const u8, m.rows() - seq.wrap(), seq.wrap(), m.stride(), seq.len(),
+                rows.start, rows.end, scores.matrix_mut()[0].as_mut_ptr(),
+                scores.matrix().stride(), &mut out_rows)
+        };
+        match st {
+            LM_OK => {}
+            LM_ERR_WRAP => panic!("not enough wrapping rows for motif of length {}", pssm.rows()),
+            e => panic!("lightmotif_b200: lm_score_f32_rows failed with status {}", e),
+        }
+    }
+}
+
+impl Score<u8, Dna, U32> for Pipeline<Dna, Cuda> {
+    fn score_rows_into<S, M>(&self, pssm: M, seq: S, rows: Range<usize>, scores: &mut StripedScores<u8, U32>)
+    where
+        S: AsRef<StripedSequence<Dna, U32>>,
+        M: AsRef<DenseMatrix<u8, <Dna as Alphabet>::K>>,
+    {
+        let seq = seq.as_ref();
+        let pssm = pssm.as_ref();
+        if seq.len() < pssm.rows() || rows.is_empty() {
+            scores.resize(0, 0);
+            return;
+        }
+        scores.resize(rows.len(), (seq.len() + 1).saturating_sub(pssm.rows()));
+        let m = seq.matrix();
+        let mut out_rows = 0usize;
+        let st = unsafe {
+            lm_score_u8_rows(
+                self.backend().ctx, 0, pssm[0].as_ptr(), pssm.rows(), pssm.stride(),
+                m[0].as_ptr() as *const u8, m.rows() - seq.wrap(), seq.wrap(), m.stride(), seq.len(),
+                rows.start, rows.end, scores.matrix_mut()[0].as_mut_ptr(),
+                scores.matrix().stride(), &mut out_rows)
+        };
+        if st == LM_ERR_WRAP {
+            panic!("not enough wrapping rows for motif of length {}", pssm.rows());
+        }
+        assert_eq!(st, LM_OK);
+    }
+}
+
+impl<A: Alphabet> Maximum<f32, U32> for Pipeline<A, Cuda> {
+    fn argmax(&self, scores: &StripedScores<f32, U32>) -> Option<MatrixCoordinates> {
+        let m = scores.matrix();
+        let mut best = LmHit::default();
+        let ptr = if m.rows() > 0 { m[0].as_ptr() } else { std::ptr::null() };
+        match unsafe { lm_argmax_f32(self.backend().ctx, ptr, m.rows(), m.stride(), LM_RULE_AVX2, &mut best) } {
+            LM_OK => Some(MatrixCoordinates::new(best.row as usize, best.col as usize)),
+            LM_EMPTY => None,
+            e => panic!("lightmotif_b200: lm_argmax_f32 failed with status {}", e),
+        }
+    }
+
+    fn max(&self, scores: &StripedScores<f32, U32>) -> Option<f32> {
+        let m = scores.matrix();
+        let mut best = 0f32;
+        let ptr = if m.rows() > 0 { m[0].as_ptr() } else { std::ptr::null() };
+        match unsafe { lm_max_f32(self.backend().ctx, ptr, m.rows(), m.stride(), &mut best) } {
+            LM_OK => Some(best),
+            LM_EMPTY => None,
+            e => panic!("lightmotif_b200: lm_max_f32 failed with status {}", e),
+        }
+    }
+}
+
+impl<A: Alphabet> Threshold<f32, U32> for Pipeline<A, Cuda> {
+    fn threshold(&self, scores: &StripedScores<f32, U32>, threshold: f32) -> Vec<MatrixCoordinates> {
+        let m = scores.matrix();
+        if m.rows() == 0 {
+            return Vec::new();
+        }
+        let mut cap = 1024usize;
+        loop {
+            let mut hits = vec![LmHit::default(); cap];
+            let mut count = 0usize;
+            let st = unsafe {
+                lm_threshold_f32(self.backend().ctx, m[0].as_ptr(), m.rows(), m.stride(), threshold,
+                                 hits.as_mut_ptr(), cap, &mut count)
+            };
+            match st {
+                LM_OK => {
+                    hits.truncate(count);
+                    return hits.iter().map(|h| MatrixCoordinates::new(h.row as usize, h.col as usize)).collect();
+                }
+                LM_ERR_OVERFLOW => cap = count,
+                e => panic!("lightmotif_b200: lm_threshold_f32 failed with status {}", e),
+            }
+        }
+    }
+}

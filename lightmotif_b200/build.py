@@ -36,16 +36,19 @@ def stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path | None = None) -> Path:
+    """Compile the library.  `extra_flags` / `out` build experiment variants
+    (tools/kbench.py) without touching the product .so."""
+    lib = out or LIB
+    if out is None and not force and not stale():
         return LIB
     nvcc = nvcc_path()
-    objdir = PKG / "_build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "_build" / (lib.stem if out else "")
+    objdir.mkdir(parents=True, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra_flags, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
@@ -56,9 +59,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}")
         (objdir / (src + ".log")).write_text(out)
         objs.append(str(obj))
-    cmd = [nvcc, *ARCH, "-shared", "-o", str(LIB), *objs]
+    cmd = [nvcc, *ARCH, "-shared", "-o", str(lib), *objs]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -10,7 +10,9 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "liblightmotif_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("LM_B200_LIB", _PKG / "liblightmotif_b200.so"))  # override: experiment builds
 
 LANES = 32
 OK, EMPTY = 0, 1

@@ -98,6 +98,14 @@ void timer_end(lm_ctx* ctx) {
   ctx->timed = true;
 }
 
+// copy `rows` rows of `width` bytes; a single flat copy when both sides are dense
+cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                      cudaMemcpyKind kind, cudaStream_t stream) {
+  if (rows == 0) return cudaSuccess;
+  if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, stream);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, stream);
+}
+
 bool valid_alphabet(int a) { return a == LM_DNA || a == LM_PROTEIN; }
 uint8_t pad_symbol(int a) { return (uint8_t)(alphabet_k(a) - 1); }
 
@@ -415,7 +423,7 @@ int lm_stripe(lm_ctx* ctx, int alphabet, const uint8_t* sym, size_t n, uint8_t* 
                        alphabet, nullptr, ctx->sm_count, ctx->stream));
   timer_end(ctx);
   ctx->launches += 1;
-  LM_TRY(cudaMemcpy2DAsync(dst, dst_stride, ctx->d_out.p, 32, 32, rows, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(copy_rows(dst, dst_stride, ctx->d_out.p, 32, 32, rows, cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   return LM_OK;
 }
@@ -437,12 +445,12 @@ int lm_configure_wrap(lm_ctx* ctx, int alphabet, uint8_t* data, size_t rows, siz
     for (size_t i = 0; i < wrap; ++i) std::memcpy(data + i * stride, fill.data(), 32);
     return LM_OK;
   }
-  LM_TRY(cudaMemcpy2DAsync(d, 32, data, stride, 32, base, cudaMemcpyHostToDevice, ctx->stream));
+  LM_TRY(copy_rows(d, 32, data, stride, 32, base, cudaMemcpyHostToDevice, ctx->stream));
   timer_begin(ctx);
   LM_TRY(launch_wrap(d, rows, rows, rows + wrap, alphabet, ctx->stream));
   timer_end(ctx);
   ctx->launches += 1;
-  LM_TRY(cudaMemcpy2DAsync(data + rows * stride, stride, d + rows * 32, 32, 32, wrap,
+  LM_TRY(copy_rows(data + rows * stride, stride, d + rows * 32, 32, 32, wrap,
                            cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   return LM_OK;
@@ -468,11 +476,11 @@ static int score_rows_host(lm_ctx* ctx, int alphabet, bool is_u8, const void* ps
   LM_CHECK(ensure(ctx, ctx->d_in, slab * 32));
   LM_CHECK(ensure(ctx, ctx->d_out, n * 32 * esz));
   LM_CHECK(upload_table(ctx, alphabet, pssm, m, pssm_stride, is_u8));
-  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32, seq + row_begin * seq_stride, seq_stride, 32, slab,
+  LM_TRY(copy_rows(ctx->d_in.p, 32, seq + row_begin * seq_stride, seq_stride, 32, slab,
                            cudaMemcpyHostToDevice, ctx->stream));
   LM_CHECK(run_score(ctx, alphabet, is_u8, MODE_STORE, (const uint8_t*)ctx->d_in.p, slab, m, 0, n,
                      ctx->d_out.p, 32, 0.f, 0, nullptr, 0));
-  LM_TRY(cudaMemcpy2DAsync(out, out_stride * esz, ctx->d_out.p, 32 * esz, 32 * esz, n,
+  LM_TRY(copy_rows(out, out_stride * esz, ctx->d_out.p, 32 * esz, 32 * esz, n,
                            cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   if (out_rows) *out_rows = n;
@@ -502,7 +510,7 @@ static int reduce_host(lm_ctx* ctx, const void* scores, bool is_u8, size_t rows,
   if (rows >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
   const size_t esz = is_u8 ? 1 : 4;
   LM_CHECK(ensure(ctx, ctx->d_in, rows * 32 * esz));
-  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
+  LM_TRY(copy_rows(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
                            cudaMemcpyHostToDevice, ctx->stream));
   uint8_t* small = (uint8_t*)ctx->d_small.p;
   LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
@@ -568,7 +576,7 @@ static int threshold_host(lm_ctx* ctx, const void* scores, bool is_u8, size_t ro
   const size_t esz = is_u8 ? 1 : 4;
   LM_CHECK(ensure(ctx, ctx->d_in, rows * 32 * esz));
   LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
-  LM_TRY(cudaMemcpy2DAsync(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
+  LM_TRY(copy_rows(ctx->d_in.p, 32 * esz, scores, stride * esz, 32 * esz, rows,
                            cudaMemcpyHostToDevice, ctx->stream));
   uint8_t* small = (uint8_t*)ctx->d_small.p;
   LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
@@ -650,7 +658,7 @@ int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t r
   LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, length, &s));
   cudaError_t e = cudaSuccess;
   if (rows + wrap)
-    e = cudaMemcpy2DAsync(s->data, 32, data, stride, 32, rows + wrap, cudaMemcpyHostToDevice, ctx->stream);
+    e = copy_rows(s->data, 32, data, stride, 32, rows + wrap, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess)
     e = cudaMemsetAsync(s->data + (rows + wrap) * 32, pad_symbol(alphabet), SLACK_ROWS * 32, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -749,7 +757,7 @@ int lm_seq_download(lm_ctx* ctx, const lm_seq* seq, uint8_t* dst, size_t dst_str
   size_t n = seq->rows + seq->wrap;
   if (n == 0) return LM_OK;
   if (!dst) return LM_ERR_INVALID_ARG;
-  LM_TRY(cudaMemcpy2DAsync(dst, dst_stride, seq->data, 32, 32, n, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(copy_rows(dst, dst_stride, seq->data, 32, 32, n, cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   return LM_OK;
 }
@@ -789,7 +797,7 @@ static int seq_score(lm_ctx* ctx, const lm_seq* seq, bool is_u8, const void* pss
   LM_CHECK(run_score(ctx, seq->alphabet, is_u8, MODE_STORE, seq->data, seq->alloc_rows, m, row_begin, row_end,
                      d_out, d_stride, 0.f, 0, nullptr, 0));
   if (!out_is_device)
-    LM_TRY(cudaMemcpy2DAsync(out, out_stride * esz, d_out, 32 * esz, 32 * esz, n, cudaMemcpyDeviceToHost, ctx->stream));
+    LM_TRY(copy_rows(out, out_stride * esz, d_out, 32 * esz, 32 * esz, n, cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   if (out_rows) *out_rows = n;
   return LM_OK;

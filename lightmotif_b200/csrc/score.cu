@@ -36,6 +36,10 @@ namespace lm {
 
 namespace {
 
+#ifndef LM_SCORE_MINBLOCKS
+#define LM_SCORE_MINBLOCKS 3
+#endif
+
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
 constexpr int RPT = 16;                 // rows (positions) per thread per tile
@@ -93,7 +97,7 @@ __device__ __forceinline__ void row_step(float (&accf)[RPT], uint32_t (&accu)[RP
 }
 
 template <int KP, int MODE, bool U8>
-__global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a, uint64_t num_tiles) {
+__global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(const ScoreArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemLayout L = smem_layout(KP, a.m_pad);
   uint32_t* table = reinterpret_cast<uint32_t*>(smem);
@@ -129,8 +133,11 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a, uint6
   uint64_t tile = blockIdx.x;
   if (tid == 0 && tile < num_tiles) stage(tile, 0);
 
-  // running per-column best (single-motif argmax); key = score_key << 32 | row
-  unsigned long long best_key = 0;
+  // running per-column best of this thread's column (single-motif argmax):
+  // score + row, updated with '>=' while rows increase => last row wins ties
+  float best_f = 0.f;
+  uint32_t best_u = 0, best_row = 0;
+  bool best_any = false;
 
   uint32_t it = 0;
   for (; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -219,30 +226,39 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a, uint6
         }
       }
       if (MODE & MODE_ARGMAX) {
-        unsigned long long k = (a.n_motifs > 1) ? 0ull : best_key;
+        float bf = best_f;
+        uint32_t bu = best_u, brow = best_row;
+        bool any = best_any;
+        if (a.n_motifs > 1) any = false;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
-          uint64_t row = my_row0 + i;
-          if (row < a.row_end) {
-            // u8: +1 so that a valid candidate never encodes to key 0 ("none")
-            uint32_t sk = U8 ? min(accu[i], 255u) + 1u : f32_to_key(accf[i]);
-            unsigned long long cand = ((unsigned long long)sk << 32) | (uint32_t)(row - a.row_begin);
-            k = cand >= k ? cand : k;  // rows increase => '>=' keeps the last row on ties
+          const uint64_t row = my_row0 + i;
+          if (row < a.row_end) {  // warp-uniform
+            const uint32_t rel = (uint32_t)(row - a.row_begin);
+            if (U8) {
+              const uint32_t s = min(accu[i], 255u);
+              if (!any || s >= bu) { bu = s; brow = rel; }
+            } else {
+              if (!any || accf[i] >= bf) { bf = accf[i]; brow = rel; }
+            }
+            any = true;
           }
         }
         if (my_row0 == a.row_begin && lane == 0 && a.row_begin < a.row_end)
           a.first_cell[q] = U8 ? min(accu[0], 255u) : __float_as_uint(accf[0]);
         if (a.n_motifs > 1) {
-          red[warp * 32 + lane] = k;
+          // u8: +1 so that a valid candidate never encodes to key 0 ("none")
+          const uint32_t sk = U8 ? bu + 1u : f32_to_key(bf);
+          red[warp * 32 + lane] = any ? (((unsigned long long)sk << 32) | brow) : 0ull;
           __syncthreads();
           if (warp == 0) {
             unsigned long long m = red[lane];
 #pragma unroll
             for (int w = 1; w < WARPS; ++w) { unsigned long long o = red[w * 32 + lane]; m = o > m ? o : m; }
-            atomicMax(&a.colkeys[(size_t)q * 32 + lane], m);
+            if (m) atomicMax(&a.colkeys[(size_t)q * 32 + lane], m);
           }
         } else {
-          best_key = k;
+          best_f = bf; best_u = bu; best_row = brow; best_any = any;
         }
       }
       if (MODE & MODE_THRESHOLD) {
@@ -277,7 +293,8 @@ __global__ void __launch_bounds__(THREADS) score_kernel(const ScoreArgs a, uint6
   }
 
   if ((MODE & MODE_ARGMAX) && a.n_motifs == 1) {
-    red[warp * 32 + lane] = best_key;
+    const uint32_t sk = U8 ? best_u + 1u : f32_to_key(best_f);
+    red[warp * 32 + lane] = best_any ? (((unsigned long long)sk << 32) | best_row) : 0ull;
     __syncthreads();
     if (warp == 0) {
       unsigned long long m = red[lane];
