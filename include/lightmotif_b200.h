@@ -105,6 +105,24 @@ uint64_t lm_ctx_kernel_launches(const lm_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) spent in the kernels
  * of the most recent scoring call */
 float lm_ctx_last_kernel_ms(const lm_ctx *ctx);
+/* Options.  LM_OPT_PRUNE controls how the FUSED calls (score+argmax,
+ * score+threshold; DNA) find their result: 0 = score every cell exactly,
+ * 1 (default) = exact filter + recheck when the cost model expects it to pay
+ * off (an integer upper bound of every cell's score is computed, only cells
+ * whose bound reaches the running threshold get the exact sequential f32 sum
+ * -- the device analogue of the reference's Scanner, scan.rs:160-250),
+ * 2 = filter whenever a plan exists.  Results are bit-identical in all modes. */
+#define LM_OPT_PRUNE 1
+/* rows scored exactly first to seed the running maximum of a filtered argmax
+ * scan (default 262144) */
+#define LM_OPT_BOOT_ROWS 2
+/* force the number of filter rows (4, 6, 8, 10, 12 or 16; 0 = planner decides) */
+#define LM_OPT_FILTER_ROWS 3
+int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
+/* statistics of the most recent fused call: out[0] = cells rechecked exactly,
+ * out[1] = tiles that fell back to exact scoring, out[2] = 1 if the filter
+ * path ran, out[3] = filter rows used */
+int lm_ctx_last_stats(const lm_ctx *ctx, uint64_t out[4]);
 
 /* --------------------------------------------- host-buffer trait mirrors */
 
@@ -219,7 +237,10 @@ int lm_seq_score_u8(lm_ctx *ctx, const lm_seq *seq, const uint8_t *dm, size_t m,
  * (scores.rs:190-192): scores never reach HBM.  Returns the cell the chosen
  * reference back-end would return, bit-identical score.  `per_column`
  * (nullable, [32]) and `first_cell` (nullable; score of cell (row_begin, 0))
- * receive what lm_argmax_merge needs for multi-GPU merging.
+ * receive what lm_argmax_merge needs for multi-GPU merging.  With LM_OPT_PRUNE
+ * active, per_column[c] is the exact column winner whenever it attains the
+ * range maximum and a valid lower bound otherwise -- which is all the tie
+ * rules and lm_argmax_merge depend on.
  * LM_EMPTY when length < m or the range is empty. */
 int lm_seq_score_argmax_f32(lm_ctx *ctx, const lm_seq *seq, const float *pssm,
                             size_t m, size_t pssm_stride, size_t row_begin,

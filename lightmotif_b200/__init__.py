@@ -248,6 +248,25 @@ class Pipeline:
     def synchronize(self):
         self._check(capi.lib().lm_ctx_synchronize(self._ctx))
 
+    def set_prune(self, mode):
+        """LM_OPT_PRUNE: 0 = score every cell, 1 = auto (default), 2 = filter whenever possible."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 1, int(mode)))
+
+    def set_filter_rows(self, r):
+        """LM_OPT_FILTER_ROWS: force the filter depth (0 = planner decides)."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 3, int(r)))
+
+    def set_boot_rows(self, rows):
+        """LM_OPT_BOOT_ROWS: rows scored exactly before the filtered argmax scan."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 2, int(rows)))
+
+    @property
+    def last_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._check(capi.lib().lm_ctx_last_stats(self._ctx, C.byref(out)))
+        return {"rechecked": int(out[0]), "overflow_tiles": int(out[1]), "pruned": bool(out[2]),
+                "filter_rows": int(out[3])}
+
     # ---- Encode ---------------------------------------------------------
     @staticmethod
     def _bytes(seq):

@@ -43,7 +43,7 @@ _lib = None
 SYMBOLS = [
     "lm_abi_version", "lm_strerror", "lm_ctx_last_error", "lm_ctx_create", "lm_ctx_create_on_stream",
     "lm_ctx_destroy", "lm_ctx_stream", "lm_ctx_synchronize", "lm_ctx_kernel_launches",
-    "lm_ctx_last_kernel_ms", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
+    "lm_ctx_last_kernel_ms", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
     "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_argmax_u8", "lm_max_u8",
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
     "lm_seq_from_striped", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
@@ -86,6 +86,8 @@ def _declare(L):
     L.lm_ctx_kernel_launches.restype = C.c_uint64
     L.lm_ctx_last_kernel_ms.argtypes = [vp]
     L.lm_ctx_last_kernel_ms.restype = C.c_float
+    L.lm_ctx_set_option.argtypes = [vp, i, i]
+    L.lm_ctx_last_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     L.lm_encode.argtypes = [vp, i, vp, sz, vp, szp]
     L.lm_encode_lossy.argtypes = [vp, i, vp, sz, vp]
     L.lm_stripe.argtypes = [vp, i, vp, sz, vp, sz]

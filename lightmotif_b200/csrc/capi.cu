@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "prune.cuh"
 #include "reduce.cuh"
 #include "score.cuh"
 #include "seqops.cuh"
@@ -32,7 +33,11 @@ struct lm_ctx {
   float last_ms = 0.f;
   uint64_t launches = 0;
   char err[256] = {0};
-  DevBuf d_in, d_out, d_table, d_small, d_hits;  // device scratch, grown on demand
+  DevBuf d_in, d_out, d_table, d_table2, d_small, d_hits;  // device scratch, grown on demand
+  int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
+  int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
+  size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
+  uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
   void* h_pin = nullptr;                          // pinned host staging
   size_t h_pin_bytes = 0;
 };
@@ -231,7 +236,7 @@ int limits_ok(int alphabet, size_t m) {
 // already uploaded to ctx->d_table
 int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* seq, size_t avail_rows,
               size_t m, size_t row_begin, size_t row_end, void* d_out, size_t out_stride,
-              float thr_f32, uint8_t thr_u8, lm_hit* d_hits, size_t cap) {
+              float thr_f32, uint8_t thr_u8, lm_hit* d_hits, size_t cap, bool standalone = true) {
   ScoreArgs a;
   a.seq = seq;
   a.avail_rows = avail_rows;
@@ -250,11 +255,39 @@ int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* se
   if (is_u8) a.thr_bits = thr_u8; else std::memcpy(&a.thr_bits, &thr_f32, 4);
   a.hits = d_hits;
   a.cap = cap;
-  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
-  timer_begin(ctx);
+  if (standalone) {
+    LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+    ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = ctx->stats[3] = 0;
+    timer_begin(ctx);
+  }
   LM_TRY(launch_score(alphabet, mode, is_u8, a, ctx->sm_count, ctx->stream));
-  timer_end(ctx);
+  if (standalone) timer_end(ctx);
   ctx->launches += 1;
+  return LM_OK;
+}
+
+// f32 table [m][8] (A,C,T,G,N,0,0,0) for the exact recheck of the pruned scan
+int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
+  const size_t bytes = m * 8 * 4;
+  LM_CHECK(ensure_pinned(ctx, bytes));
+  LM_CHECK(ensure(ctx, ctx->d_table2, bytes));
+  float* h = (float*)ctx->h_pin;
+  for (size_t j = 0; j < m; ++j)
+    for (int a = 0; a < 8; ++a) h[j * 8 + a] = a < 5 ? pssm[j * stride + a] : 0.f;
+  LM_TRY(cudaMemcpyAsync(ctx->d_table2.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+
+int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
+  unsigned long long st[2] = {0, 0};
+  LM_TRY(cudaMemcpyAsync(st, (uint8_t*)ctx->d_small.p + 272, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->stats[0] = st[0];
+  ctx->stats[1] = st[1];
+  ctx->stats[2] = 1;
+  ctx->stats[3] = (uint64_t)plan.r;
   return LM_OK;
 }
 
@@ -343,7 +376,7 @@ void lm_ctx_destroy(lm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_small, &ctx->d_hits})
+  for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits})
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -361,6 +394,29 @@ int lm_ctx_synchronize(lm_ctx* ctx) {
 }
 
 uint64_t lm_ctx_kernel_launches(const lm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
+  if (!ctx) return LM_ERR_INVALID_ARG;
+  if (option == LM_OPT_PRUNE && value >= 0 && value <= 2) {
+    ctx->opt_prune = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_FILTER_ROWS && value >= 0 && value <= 16) {
+    ctx->opt_filter_rows = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_BOOT_ROWS && value >= 1) {
+    ctx->opt_boot_rows = (size_t)value;
+    return LM_OK;
+  }
+  return LM_ERR_INVALID_ARG;
+}
+
+int lm_ctx_last_stats(const lm_ctx* ctx, uint64_t out[4]) {
+  if (!ctx || !out) return LM_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = ctx->stats[i];
+  return LM_OK;
+}
 
 float lm_ctx_last_kernel_ms(const lm_ctx* ctx) {
   if (!ctx || !ctx->timed) return 0.f;
@@ -826,8 +882,42 @@ int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, s
   if (st != LM_OK) return st;
   LM_CHECK(limits_ok(seq->alphabet, m));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
-  LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin, row_end,
-                     nullptr, 0, 0.f, 0, nullptr, 0));
+  const size_t n_rows = row_end - row_begin;
+  PrunePlan plan;
+  if (ctx->opt_prune && seq->alphabet == LM_DNA && n_rows > 2 * ctx->opt_boot_rows) {
+    const double npos = (double)n_rows * 32.0;
+    plan = plan_prune(pssm, m, pssm_stride, estimate_max_score(pssm, m, pssm_stride, npos), true, npos,
+                      ctx->opt_filter_rows);
+    if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
+  }
+  if (plan.ok) {
+    // 1. exact scan of the first rows seeds the per-column winners (= the running maximum)
+    // 2. filter + exact recheck over the rest, raising the maximum as it goes
+    LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
+    uint8_t* small = (uint8_t*)ctx->d_small.p;
+    LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+    timer_begin(ctx);
+    LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin,
+                       row_begin + ctx->opt_boot_rows, nullptr, 0, 0.f, 0, nullptr, 0, false));
+    PruneArgs pa;
+    pa.seq = seq->data;
+    pa.avail_rows = seq->alloc_rows;
+    pa.row_begin = row_begin;
+    pa.row_first = row_begin + ctx->opt_boot_rows;
+    pa.row_end = row_end;
+    pa.pad_sym = pad_symbol(seq->alphabet);
+    pa.table = (const float*)ctx->d_table2.p;
+    pa.plan = plan;
+    pa.colkeys = (unsigned long long*)small;
+    pa.stats = (unsigned long long*)(small + 272);
+    LM_TRY(launch_prune(false, pa, ctx->sm_count, ctx->stream));
+    timer_end(ctx);
+    ctx->launches += 1;
+    LM_CHECK(fetch_stats(ctx, plan));
+  } else {
+    LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin, row_end,
+                       nullptr, 0, 0.f, 0, nullptr, 0));
+  }
   ColKeys ck;
   LM_CHECK(fetch_colkeys(ctx, &ck));
   lm_colwin cw[32];
@@ -849,8 +939,39 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
   LM_CHECK(limits_ok(seq->alphabet, m));
   LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
-  LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_THRESHOLD, seq->data, seq->alloc_rows, m, row_begin, row_end,
-                     nullptr, 0, t, 0, (lm_hit*)ctx->d_hits.p, cap));
+  PrunePlan plan;
+  if (ctx->opt_prune && seq->alphabet == LM_DNA && row_end - row_begin > 4096) {
+    plan = plan_prune(pssm, m, pssm_stride, (double)t, false, (double)(row_end - row_begin) * 32.0,
+                      ctx->opt_filter_rows);
+    if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
+  }
+  if (plan.ok) {
+    LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
+    uint8_t* small = (uint8_t*)ctx->d_small.p;
+    LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+    PruneArgs pa;
+    pa.seq = seq->data;
+    pa.avail_rows = seq->alloc_rows;
+    pa.row_begin = row_begin;
+    pa.row_first = row_begin;
+    pa.row_end = row_end;
+    pa.pad_sym = pad_symbol(seq->alphabet);
+    pa.table = (const float*)ctx->d_table2.p;
+    pa.plan = plan;
+    pa.thr = t;
+    pa.hits = (lm_hit*)ctx->d_hits.p;
+    pa.cap = cap;
+    pa.count = (unsigned long long*)(small + 264);
+    pa.stats = (unsigned long long*)(small + 272);
+    timer_begin(ctx);
+    LM_TRY(launch_prune(true, pa, ctx->sm_count, ctx->stream));
+    timer_end(ctx);
+    ctx->launches += 1;
+    LM_CHECK(fetch_stats(ctx, plan));
+  } else {
+    LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_THRESHOLD, seq->data, seq->alloc_rows, m, row_begin, row_end,
+                       nullptr, 0, t, 0, (lm_hit*)ctx->d_hits.p, cap));
+  }
   return fetch_hits(ctx, hits, cap, count);
 }
 

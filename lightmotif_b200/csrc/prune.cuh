@@ -1,0 +1,68 @@
+// prune.cuh -- exact filter + recheck ("branch and bound") scan, DNA only.
+//
+// For the FUSED outputs (argmax, threshold hits) the per-position f32 scores
+// never leave the chip, so only positions that can matter need the exact
+// sequential f32 sum.  A cheap integer UPPER BOUND of the score is computed for
+// every position (4 positions per 32-bit register, PRMT byte look-ups); only
+// positions whose bound reaches the current threshold are rescored exactly
+// (same sequential order as the reference => bit-identical results).  This is
+// the reference's own Scanner idea (lightmotif/src/scan.rs:160-250: u8
+// DiscreteMatrix prefilter, f32 recheck of candidates) rebuilt for the GPU.
+#pragma once
+
+#include "common.cuh"
+
+namespace lm {
+
+constexpr int PRUNE_MAX_M = 256;
+
+// Host-built plan for one DNA PSSM.
+struct PrunePlan {
+  int m = 0;          // motif rows
+  int r = 0;          // filter rows (contiguous block [j0, j0 + r)), one of 4,6,8,10,12,16
+  int j0 = 0;
+  uint32_t tab_lo[16];  // per filter row: bytes = q[j][A,C,T,G]
+  uint32_t tab_hi[16];  // per filter row: byte 0 = q[j][N], bytes 1..3 = 0
+  int smax = 0;         // max attainable sum of q over the filter rows (<= 127)
+  // UB(p) = c0 + delta * sum_q(p)  >=  real-valued score(p);  fp32 score <= real + eps
+  double c0 = 0, delta = 1, eps = 0;
+  double est_pass_rate = 1.0;  // under a uniform background at the planning threshold
+  bool ok = false;
+};
+
+// Plan the filter for `pssm` ([m][stride] f32, DNA: columns A,C,T,G,N).
+// `t_plan` is the threshold the filter is expected to run at (the user's
+// threshold, or an estimate of the final maximum for argmax scans over
+// `n_positions` cells).  Returns plan.ok == false when pruning is not
+// expected to pay off (the caller then uses the exact-everywhere kernel).
+PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, bool t_is_estimate,
+                     double n_positions, int force_r = 0);
+
+// Score quantile helper used for argmax planning: the score t such that the
+// expected number of cells with score >= t among n uniform-random positions is ~1.
+double estimate_max_score(const float* pssm, size_t m, size_t stride, double n_positions);
+
+struct PruneArgs {
+  const uint8_t* seq = nullptr;  // [avail_rows][32]
+  uint64_t avail_rows = 0;
+  uint64_t row_begin = 0;        // first row of the scored range (positions are relative to it)
+  uint64_t row_first = 0;        // first row THIS launch scans (>= row_begin; rows before were bootstrapped)
+  uint64_t row_end = 0;
+  uint8_t pad_sym = 4;
+  const float* table = nullptr;  // device: [m][8] f32 (A,C,T,G,N,0,0,0)
+  PrunePlan plan;
+  // argmax mode: colkeys[32] holds the running per-column winners (read for the
+  // dynamic threshold, updated with atomicMax)
+  unsigned long long* colkeys = nullptr;
+  // threshold mode
+  float thr = 0.f;
+  lm_hit* hits = nullptr;
+  unsigned long long cap = 0;
+  unsigned long long* count = nullptr;
+  // statistics: [0] candidates rechecked, [1] tiles that overflowed to the exact fallback
+  unsigned long long* stats = nullptr;
+};
+
+cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream);
+
+}  // namespace lm

@@ -1,0 +1,154 @@
+"""The filter + recheck ("pruned") fused scans must return exactly what the
+score-every-cell path returns: same cell, bit-identical score, same hit list --
+including adversarial inputs (low complexity, N runs, ties, -inf weights)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lm():
+    import lightmotif_b200 as lm
+    return lm
+
+
+@pytest.fixture()
+def dna(lm):
+    p = lm.Pipeline.cuda(lm.DNA)
+    yield p
+    p.close()
+
+
+def random_pssm(rng, m, kind):
+    if kind == "logodds":
+        counts = rng.integers(0, 50, size=(m, 5)).astype(np.uint32)
+        counts[:, 4] = 0
+        counts[rng.integers(0, m, m // 2), rng.integers(0, 4, m // 2)] += 400  # informative rows
+        return O.pssm_from_counts(O.DNA, counts, 0.1)
+    if kind == "neginf":
+        counts = rng.integers(0, 3, size=(m, 5)).astype(np.uint32)
+        counts[:, 4] = 0
+        counts[np.arange(m), rng.integers(0, 4, m)] += 30
+        return O.pssm_from_counts(O.DNA, counts, 0.0)  # zero counts -> -inf cells
+    if kind == "ints":  # many exact ties
+        p = rng.integers(-3, 3, size=(m, 5)).astype(np.float32)
+        p[:, 4] = -np.inf
+        return p
+    if kind == "finite_n":  # N column finite
+        p = rng.normal(0, 2, size=(m, 5)).astype(np.float32)
+        return p
+    raise ValueError(kind)
+
+
+def make_sequence(rng, n, kind):
+    if kind == "uniform":
+        return rng.integers(0, 4, n).astype(np.uint8)
+    if kind == "with_n":
+        s = rng.integers(0, 4, n).astype(np.uint8)
+        for _ in range(20):
+            a = rng.integers(0, n)
+            s[a:a + rng.integers(1, 3000)] = 4
+        return s
+    if kind == "lowcomplexity":
+        s = rng.integers(0, 4, n).astype(np.uint8)
+        a = n // 3
+        s[a:a + 200000] = 0          # poly-A
+        s[2 * a:2 * a + 100000] = np.tile(np.array([1, 3], np.uint8), 50000)  # CGCG...
+        return s
+    raise ValueError(kind)
+
+
+def compare(pli, seq, pssm, thresholds):
+    res = {}
+    for mode in (0, 2):
+        pli.set_prune(mode)
+        res[mode] = {"argmax": {r: seq.score_argmax(pssm, rule=r) for r in (0, 1, 2)},
+                     "stats": pli.last_stats,
+                     "thr": {t: seq.score_threshold(pssm, t) for t in thresholds}}
+    for r in (0, 1, 2):
+        assert res[0]["argmax"][r] == res[2]["argmax"][r], (r, res[0]["argmax"][r], res[2]["argmax"][r])
+    for t in thresholds:
+        assert res[0]["thr"][t] == res[2]["thr"][t], t
+    return res
+
+
+@pytest.mark.parametrize("m,pk", [(4, "logodds"), (6, "ints"), (8, "logodds"), (11, "neginf"), (15, "logodds"),
+                                  (20, "logodds"), (20, "finite_n"), (21, "ints"), (33, "logodds")])
+@pytest.mark.parametrize("sk", ["uniform", "with_n", "lowcomplexity"])
+def test_pruned_equals_exact(dna, m, pk, sk):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"{m}-{pk}-{sk}".encode()))
+    n = 1_500_003
+    pssm = random_pssm(rng, m, pk)
+    sym = make_sequence(rng, n, sk)
+    seq = dna.sequence_from_symbols(sym, m - 1)
+    dna.set_boot_rows(4096)
+    # thresholds: high (few hits), medium, and one so low that tiles overflow to the exact fallback
+    dna.set_prune(0)
+    ref = seq.score(pssm)
+    finite = ref[np.isfinite(ref)]
+    ts = [float(np.quantile(finite, q)) for q in (0.99999, 0.999, 0.5)]
+    res = compare(dna, seq, pssm, ts)
+    # and against the CPU oracle on the materialised scores
+    for r in (0, 1, 2):
+        rr, cc = O.argmax(ref, r)
+        got = res[2]["argmax"][r]
+        assert (got["row"], got["col"]) == (rr, cc)
+        assert np.float32(got["score"]).view(np.uint32) == ref[rr, cc].view(np.uint32)
+    ro, co = O.threshold(ref, ts[0])
+    assert [(h["row"], h["col"]) for h in res[2]["thr"][ts[0]]] == list(zip(ro.tolist(), co.tolist()))
+
+
+def test_pruned_actually_prunes_and_matches_on_rest(dna, jaspar):
+    pssm = O.pssm_from_counts(O.DNA, jaspar["rest"], 0.1)
+    n = 64_000_000
+    seq = dna.sequence_synthetic(n, len(pssm) - 1)
+    dna.set_prune(0)
+    exact = seq.score_argmax(pssm, with_columns=True)
+    assert not dna.last_stats["pruned"]
+    dna.set_prune(1)  # auto: the cost model must pick the filter for this motif
+    pr = seq.score_argmax(pssm, with_columns=True)
+    st = dna.last_stats
+    assert st["pruned"] and st["overflow_tiles"] == 0 and st["rechecked"] < n // 100
+    assert {k: pr[k] for k in ("row", "col", "position", "score")} == {k: exact[k] for k in ("row", "col", "position", "score")}
+    assert pr["first_cell"] == exact["first_cell"]
+    # per-column winners: exact wherever they attain the maximum, lower bounds elsewhere
+    for (r0, s0, v0), (r1, s1, v1) in zip(exact["columns"], pr["columns"]):
+        assert v1 and s1 <= s0
+        if s0 == exact["score"]:
+            assert (r1, s1) == (r0, s0)
+    for t in (12.0, 18.0):
+        dna.set_prune(0)
+        a = seq.score_threshold(pssm, t)
+        dna.set_prune(1)
+        b = seq.score_threshold(pssm, t)
+        assert dna.last_stats["pruned"] and a == b and len(a) > 0
+    # sub-range scans
+    dna.set_boot_rows(8192)
+    lo, hi = 123456, 1_900_000
+    dna.set_prune(0)
+    a = seq.score_argmax(pssm, rows=(lo, hi))
+    dna.set_prune(2)
+    b = seq.score_argmax(pssm, rows=(lo, hi))
+    assert a == b and dna.last_stats["pruned"]
+
+
+def test_all_equal_sequence_ties(dna):
+    """Every cell ties: the filter passes everything, tiles fall back to exact
+    scoring, and the tie rules still pick the reference's cell."""
+    n = 400_000
+    sym = np.zeros(n, np.uint8)
+    rng = np.random.default_rng(5)
+    pssm = random_pssm(rng, 12, "logodds")
+    seq = dna.sequence_from_symbols(sym, 11)
+    dna.set_boot_rows(1024)
+    dna.set_prune(0)
+    ref = seq.score(pssm)
+    for r in (0, 1, 2):
+        dna.set_prune(2)
+        got = seq.score_argmax(pssm, rule=r)
+        rr, cc = O.argmax(ref, r)
+        assert (got["row"], got["col"]) == (rr, cc), r

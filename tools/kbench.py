@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--m", type=int, default=20)
     ap.add_argument("--mode", default="argmax")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--prune", type=int, default=1)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--thr", type=float, default=18.0)
     a = ap.parse_args()
     z = np.load(Path(__file__).resolve().parent.parent / "tests/golden/jaspar2024.npz")
     pssm = O.pssm_from_counts(O.DNA, z["rest"], 0.1)
@@ -29,6 +32,8 @@ def main():
         rng = np.random.default_rng(a.m)
         pssm = np.concatenate([pssm] * (a.m // 20 + 1))[: a.m].copy()
     pli = lm.Pipeline.cuda(lm.DNA)
+    pli.set_prune(a.prune)
+    pli.set_filter_rows(a.rows)
     seq = pli.sequence_synthetic(a.bp, a.m - 1)
     times = []
     res = None
@@ -36,11 +41,11 @@ def main():
         if a.mode == "argmax":
             res = seq.score_argmax(pssm)
         elif a.mode == "threshold":
-            res = len(seq.score_threshold(pssm, 18.0))
+            res = len(seq.score_threshold(pssm, a.thr))
         times.append(pli.last_kernel_ms)
     best = min(times)
     print(f"{a.tag:24s} mode={a.mode} m={a.m} bp={a.bp:.3g}  best {best:.3f} ms  median {np.median(times):.3f} ms  "
-          f"-> {a.bp / best / 1e6:.1f} Gbp/s  result={res}")
+          f"-> {a.bp / best / 1e6:.1f} Gbp/s  result={res} stats={pli.last_stats}")
 
 
 if __name__ == "__main__":
