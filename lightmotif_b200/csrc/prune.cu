@@ -1,10 +1,10 @@
 // prune.cu -- exact filter + recheck scan (DNA), see prune.cuh.
 //
-// Kernel (one CTA = 8 warps, tile = 800 striped rows x 32 columns = 25 600
+// Kernel (one CTA = 8 warps, tile = 672 striped rows x 32 columns = 21 504
 // positions, staged from HBM with one bulk-TMA copy, double-buffered):
 //
 //  filter   lane = (column quad q = lane & 7, row group g = lane >> 3); a thread
-//           walks PL (25) consecutive rows of its 4 columns.  One LDS.32 per row
+//           walks PL (21) consecutive rows of its 4 columns.  One LDS.32 per row
 //           yields 4 symbols (4 adjacent columns = 4 independent positions);
 //           3 ALU ops turn them into a PRMT selector that is reused by all R
 //           filter rows:   acc = bias + sum_k PRMT(table[k], selector[i + k])
@@ -35,7 +35,7 @@ namespace {
 constexpr int PW = 8;
 constexpr int PT = PW * 32;
 #ifndef LM_PRUNE_PL
-#define LM_PRUNE_PL 25
+#define LM_PRUNE_PL 21
 #endif
 #ifndef LM_PRUNE_MINBLOCKS
 #define LM_PRUNE_MINBLOCKS 3
@@ -63,9 +63,12 @@ __host__ __device__ inline PSmem psmem(int m) {
 
 struct Misc {
   uint64_t bars[2];
-  uint32_t qcount[2];  // double-buffered queue length (saves one barrier per tile)
+  unsigned long long next_tile[2];  // dynamically scheduled tile staged in each buffer
+  uint32_t qcount[2];               // double-buffered queue length (saves one barrier per tile)
   uint32_t bias4;
   float thr;
+  uint32_t thr_key;                 // threshold key the bias was computed for
+  uint32_t pad;
 };
 
 // raw PRMT (the __byte_perm intrinsic masks the selector with 0x7777 first)
@@ -109,6 +112,10 @@ __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* t
   for (int j = 0; j < m; ++j) s = __fadd_rn(s, tab[j * 8 + p[j * 32]]);
   return s;
 }
+
+#ifdef LM_PRUNE_DEBUG
+__device__ unsigned long long g_dbg[2048][4];
+#endif
 
 template <int R, bool THR>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
@@ -159,26 +166,40 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     __syncthreads();
   }
 
-  uint64_t tile = blockIdx.x;
-  if (tid == 0 && tile < num_tiles) stage(tile, 0);
+  // dynamic tile scheduling: CTAs pull tiles from a global counter so that all of them finish
+  // together (with a static split the first-launched CTA of an SM runs ahead and the SM ends with
+  // too few warps); the tile for iteration it+1 is claimed when its prefetch is issued
+  auto claim = [&]() -> unsigned long long { return atomicAdd(&a.stats[2], 1ull); };
+  if (tid == 0) {
+    unsigned long long t0 = claim();
+    misc->next_tile[0] = t0;
+    misc->thr_key = 0xffffffffu;
+    if (t0 < num_tiles) stage(t0, 0);
+  }
   unsigned long long n_cand = 0, n_over = 0;
+#ifdef LM_PRUNE_DEBUG
+  unsigned long long dbg_t0 = 0, dbg_g0 = 0;
+  if (tid == 0) { dbg_t0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_g0)); }
+#endif
+  // threshold key prefetched one tile ahead (L2 latency off the critical path; stale is safe)
+  uint32_t sk_next = 0;
+  if (!THR && warp == 0) sk_next = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
+  __syncthreads();
 
   uint32_t it = 0;
-  for (; tile < num_tiles; tile += gridDim.x, ++it) {
+  for (;; ++it) {
     const int buf = it & 1;
-    // ---- current threshold -> byte bias
+    const uint64_t tile = misc->next_tile[buf];
+    if (tile >= num_tiles) break;
+    // ---- current threshold -> byte bias (recomputed only when the threshold moved)
     if (warp == 0) {
-      float t;
-      if (THR) {
-        t = a.thr;
-      } else {
-        unsigned long long k = a.colkeys[lane];  // plain load: a stale (lower) value is safe
-        uint32_t sk = (uint32_t)(k >> 32);
+      uint32_t sk = sk_next;
+      if (!THR) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
-        t = sk ? key_to_f32(sk) : -INFINITY;
       }
-      if (lane == 0) {
+      if (lane == 0 && (THR ? it == 0 : sk != misc->thr_key)) {
+        const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
         // sum_q >= qthr is implied by fp32score >= t (see header); -1 guards the division
         double need = ((double)t - a.plan.eps - a.plan.c0) / a.plan.delta;
         int bias;
@@ -191,6 +212,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         }
         misc->bias4 = (uint32_t)bias * 0x01010101u;
         misc->thr = t;
+        misc->thr_key = sk;
       }
     }
     mbar_wait(&misc->bars[buf], (it >> 1) & 1);
@@ -206,9 +228,13 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     }
     __syncthreads();  // (A) tile + bias visible; every thread is done with the previous tile
     {
-      // prefetch the next tile into the other buffer (free since barrier A)
-      const uint64_t next = tile + gridDim.x;
-      if (tid == 0 && next < num_tiles) stage(next, buf ^ 1);
+      // claim + prefetch the next tile into the other buffer (free since barrier A)
+      if (tid == 0) {
+        unsigned long long nt = claim();
+        misc->next_tile[buf ^ 1] = nt;
+        if (nt < num_tiles) stage(nt, buf ^ 1);
+      }
+      if (!THR && warp == 0) sk_next = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
     }
     const uint32_t bias4 = misc->bias4;
     const float thr = misc->thr;
@@ -270,6 +296,17 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       if (tid == 0) n_over += 1;
     }
   }
+#ifdef LM_PRUNE_DEBUG
+  if (tid == 0 && blockIdx.x < 2048) {
+    unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    unsigned long long g1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+    g_dbg[blockIdx.x][0] = clock64() - dbg_t0;
+    g_dbg[blockIdx.x][1] = n_cand;
+    g_dbg[blockIdx.x][2] = smid | ((unsigned long long)it << 32);
+    g_dbg[blockIdx.x][3] = dbg_g0 | 0;  // start time (ns)
+    (void)g1;
+  }
+#endif
   if (tid == 0 && a.stats) {
     if (n_cand) atomicAdd(&a.stats[0], n_cand);
     if (n_over) atomicAdd(&a.stats[1], n_over);
@@ -380,7 +417,7 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
   Rows r;
   if (m < 4 || m > PRUNE_MAX_M || !load_rows(pssm, m, stride, r)) return best;
   (void)n_positions;
-  if (t_is_estimate) t_plan -= 3.0;  // the running maximum starts lower than the final one
+  if (t_is_estimate) t_plan -= 1.0;  // the running maximum spends most of the scan just below the final one
   double abs_sum = 0;                // sum_j max_a |w| over finite entries, for the fp32 error bound
   double max_total = 0;
   for (size_t j = 0; j < m; ++j) {
@@ -395,8 +432,8 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
   static const double CS[] = {4.0, 6.0, 8.0, 12.0, CLAMP_FLOOR};
   double best_cost = 1e300;
   // cost model calibrated on B200 (profiles/README.md): per position, a filter of R rows costs
-  // ~(1.5 R + 12) / 4 issue slots, a queued candidate ~1000 (divergent recheck), exact scoring ~55
-  const double EXACT_COST = 55.0, RECHECK_COST = 1000.0;
+  // ~(1.5 R + 15.6) / 4 issue slots, a queued candidate ~870 (divergent recheck), exact scoring ~55
+  const double EXACT_COST = 55.0, RECHECK_COST = 870.0;
   for (int R : RS) {
     if (R > (int)m || (force_r && R != force_r)) continue;
     for (int j0 = 0; j0 + R <= (int)m; ++j0) {
@@ -450,7 +487,7 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
           pass = 0;
           for (int i = qthr; i < 128; ++i) pass += d[i];
         }
-        const double cost = (1.5 * R + 12.0) / 4.0 + pass * RECHECK_COST;
+        const double cost = (1.5 * R + 15.6) / 4.0 + pass * RECHECK_COST;
         if (cost < best_cost) {
           best_cost = cost;
           best.m = (int)m;
@@ -474,6 +511,13 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
   best.ok = best_cost < EXACT_COST && best.r > 0;
   return best;
 }
+
+#ifdef LM_PRUNE_DEBUG
+extern "C" void lm_debug_dump(unsigned long long* out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 4 * n);
+}
+#endif
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream) {
   return threshold_mode ? launch_r<true>(a, sm_count, stream) : launch_r<false>(a, sm_count, stream);

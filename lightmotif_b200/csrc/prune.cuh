@@ -59,7 +59,8 @@ struct PruneArgs {
   lm_hit* hits = nullptr;
   unsigned long long cap = 0;
   unsigned long long* count = nullptr;
-  // statistics: [0] candidates rechecked, [1] tiles that overflowed to the exact fallback
+  // statistics: [0] candidates rechecked, [1] tiles that overflowed to the exact fallback;
+  // [2] is the dynamic tile counter (zero-initialised)
   unsigned long long* stats = nullptr;
 };
 
