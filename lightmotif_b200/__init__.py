@@ -22,7 +22,7 @@ from .capi import (DNA, PROTEIN, RULE_AVX2, RULE_GENERIC, RULE_SSE2, LANES, ColW
 
 __all__ = ["Pipeline", "DeviceSequence", "InvalidSymbol", "UnsupportedBackend", "MatrixCoordinates",
            "DNA", "PROTEIN", "RULE_GENERIC", "RULE_AVX2", "RULE_SSE2", "LANES", "alphabet_k",
-           "pad_pssm", "aligned_empty"]
+           "pad_pssm", "aligned_empty", "argmax_merge", "COLWIN_DTYPE"]
 
 
 class InvalidSymbol(ValueError):
@@ -160,7 +160,10 @@ class DeviceSequence:
         if st == capi.EMPTY:
             return None
         res = _hit(best)
-        if with_columns:
+        if with_columns == "numpy":  # zero-copy view of the lm_colwin[32] array (fast path for dist)
+            res["columns"] = np.frombuffer(cols, dtype=COLWIN_DTYPE).copy()
+            res["first_cell"] = float(np.float32(fc.value))
+        elif with_columns:
             res["columns"] = [(int(c.row), float(np.float32(c.score)), int(c.valid)) for c in cols]
             res["first_cell"] = float(np.float32(fc.value))
         return res
@@ -393,16 +396,23 @@ class Pipeline:
         return self._seq(h)
 
 
+COLWIN_DTYPE = np.dtype([("row", np.uint64), ("score", np.float32), ("valid", np.uint32)])  # == lm_colwin
+
+
 def argmax_merge(parts, row_offsets, first_cell, total_rows, rule=RULE_AVX2):
-    """lm_argmax_merge: parts = list (one per slab) of 32 (row, score, valid)."""
-    n = len(parts)
-    arr = (ColWin * (n * LANES))()
-    for p, cols in enumerate(parts):
-        for c, (row, score, valid) in enumerate(cols):
-            arr[p * LANES + c] = ColWin(int(row), float(score), int(valid))
-    offs = np.asarray(row_offsets, dtype=np.uint64)
+    """lm_argmax_merge.  parts: [n_slabs, 32] array of COLWIN_DTYPE, or a list
+    (one per slab) of 32 (row, score, valid) tuples."""
+    if isinstance(parts, np.ndarray) and parts.dtype == COLWIN_DTYPE:
+        arr = np.ascontiguousarray(parts)
+    else:
+        arr = np.zeros((len(parts), LANES), dtype=COLWIN_DTYPE)
+        for p, cols in enumerate(parts):
+            for c, (row, score, valid) in enumerate(cols):
+                arr[p, c] = (int(row), float(score), int(valid))
+    offs = np.ascontiguousarray(row_offsets, dtype=np.uint64)
     best = Hit()
-    st = capi.lib().lm_argmax_merge(arr, n, _ptr(offs), float(first_cell), int(total_rows), rule, C.byref(best))
+    st = capi.lib().lm_argmax_merge(arr.ctypes.data_as(C.POINTER(ColWin)), arr.shape[0], _ptr(offs),
+                                    float(first_cell), int(total_rows), rule, C.byref(best))
     if st < 0:
         raise LightmotifError(st)
     return None if st == capi.EMPTY else _hit(best)
