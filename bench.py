@@ -201,13 +201,31 @@ def run_ours(args):
     positions = (r1 - r0) * 32  # cells scored per step on this rank (1 byte each)
 
     xchg = lmdist.WinnerExchange(device=dev) if world > 1 else None
+    xstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    if world > 1:
+        pli.set_reserve_sms(1)  # one SM stays free so the all-gather of scan k overlaps scan k+1
 
-    def step():
-        res = seq.score_argmax(pssm, rule=lm.RULE_AVX2, with_columns="numpy")
+    # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners.  Steps are
+    # software-pipelined one deep: scan k+1 is enqueued before the host finishes / exchanges scan k.
+    def launch(k):
+        seq.score_argmax_launch(pssm, slot=k & 1)
+
+    def finish(k):
+        res = seq.score_argmax_finish(slot=k & 1, rule=lm.RULE_AVX2, with_columns="numpy")
         kms = pli.last_kernel_ms
         if world > 1:  # global argmax: all-gather of per-column winners over NVLink, then merge
-            res = xchg.merge(res, r0, rows_global, lm.RULE_AVX2)
+            with torch.cuda.stream(xstream):
+                res = xchg.merge(res, r0, rows_global, lm.RULE_AVX2)
         return res, kms
+
+    def run_steps(n):
+        out = []
+        launch(0)
+        for k in range(n):
+            if k + 1 < n:
+                launch(k + 1)
+            out.append(finish(k))
+        return out
 
     def sync_all():
         torch.cuda.synchronize()
@@ -215,8 +233,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    run_steps(max(args.warmup, 1))
     stats = pli.last_stats
     sampler = ClockSampler(local)
     launches0 = pli.kernel_launches
@@ -224,14 +241,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     e0.record(stream)
-    for _ in range(args.steps):
-        res, kms = step()
-        kernel_ms.append(kms)
+    results = run_steps(args.steps)
     e1.record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    res = results[-1][0]
+    kernel_ms = [r[1] for r in results]
     ms = e0.elapsed_time(e1)
     launches = pli.kernel_launches - launches0
     if world > 1:

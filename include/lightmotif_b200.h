@@ -118,6 +118,10 @@ float lm_ctx_last_kernel_ms(const lm_ctx *ctx);
 #define LM_OPT_BOOT_ROWS 2
 /* force the number of filter rows (4, 6, 8, 10, 12 or 16; 0 = planner decides) */
 #define LM_OPT_FILTER_ROWS 3
+/* leave this many SMs out of the persistent scoring grids so that a concurrent
+ * small kernel (the NCCL all-gather of the previous scan's winners) can run
+ * next to a scan (default 0) */
+#define LM_OPT_RESERVE_SMS 4
 int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
 /* statistics of the most recent fused call: out[0] = cells rechecked exactly,
  * out[1] = tiles that fell back to exact scoring, out[2] = 1 if the filter
@@ -246,6 +250,18 @@ int lm_seq_score_argmax_f32(lm_ctx *ctx, const lm_seq *seq, const float *pssm,
                             size_t m, size_t pssm_stride, size_t row_begin,
                             size_t row_end, int rule, lm_hit *best,
                             lm_colwin *per_column, float *first_cell);
+/* Split form of lm_seq_score_argmax_f32 for pipelining: `launch` only enqueues
+ * the kernels and the copy of the 300-byte result block (slot = 0 or 1, so two
+ * calls can be in flight: e.g. the scan of motif k+1 runs while the host merges
+ * / all-gathers the winners of motif k); `finish` waits for that slot and
+ * returns exactly what the one-shot call returns. */
+int lm_seq_score_argmax_f32_launch(lm_ctx *ctx, const lm_seq *seq,
+                                   const float *pssm, size_t m,
+                                   size_t pssm_stride, size_t row_begin,
+                                   size_t row_end, int slot);
+int lm_seq_score_argmax_f32_finish(lm_ctx *ctx, int slot, int rule,
+                                   lm_hit *best, lm_colwin *per_column,
+                                   float *first_cell);
 /* FUSED score + Threshold::threshold (scores.rs:207-213): all cells >= t of
  * the scored rows, row-major order, exact f32 scores. */
 int lm_seq_score_threshold_f32(lm_ctx *ctx, const lm_seq *seq,

@@ -168,6 +168,30 @@ class DeviceSequence:
             res["first_cell"] = float(np.float32(fc.value))
         return res
 
+    def score_argmax_launch(self, pssm, slot=0, rows=None):
+        """Enqueue a fused argmax scan (lm_seq_score_argmax_f32_launch); pair with score_argmax_finish."""
+        p, stride = pad_pssm(pssm, self.alphabet)
+        b, e = self._rng(rows)
+        self._pli._check(capi.lib().lm_seq_score_argmax_f32_launch(self._pli._ctx, self._h, _ptr(p), p.shape[0],
+                                                                   stride, b, e, slot))
+
+    def score_argmax_finish(self, slot=0, rule=RULE_AVX2, with_columns=False):
+        best = Hit()
+        cols = (ColWin * LANES)()
+        fc = C.c_float(0)
+        st = capi.lib().lm_seq_score_argmax_f32_finish(self._pli._ctx, slot, rule, C.byref(best), cols, C.byref(fc))
+        self._pli._check(st)
+        if st == capi.EMPTY:
+            return None
+        res = _hit(best)
+        if with_columns == "numpy":
+            res["columns"] = np.frombuffer(cols, dtype=COLWIN_DTYPE).copy()
+            res["first_cell"] = float(np.float32(fc.value))
+        elif with_columns:
+            res["columns"] = [(int(c.row), float(np.float32(c.score)), int(c.valid)) for c in cols]
+            res["first_cell"] = float(np.float32(fc.value))
+        return res
+
     def score_threshold(self, pssm, t, rows=None, cap=1 << 20):
         """Fused score + Threshold::threshold -> list of hits in row-major order."""
         p, stride = pad_pssm(pssm, self.alphabet)
@@ -258,6 +282,10 @@ class Pipeline:
     def set_filter_rows(self, r):
         """LM_OPT_FILTER_ROWS: force the filter depth (0 = planner decides)."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 3, int(r)))
+
+    def set_reserve_sms(self, n):
+        """LM_OPT_RESERVE_SMS: SMs left free for concurrent kernels (NCCL)."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 4, int(n)))
 
     def set_boot_rows(self, rows):
         """LM_OPT_BOOT_ROWS: rows scored exactly before the filtered argmax scan."""

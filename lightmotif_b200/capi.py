@@ -48,7 +48,8 @@ SYMBOLS = [
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
     "lm_seq_from_striped", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
-    "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_threshold_f32",
+    "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
+    "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
     "lm_seq_score_argmax_f32_batch", "lm_argmax_merge",
 ]
 
@@ -115,6 +116,8 @@ def _declare(L):
     L.lm_seq_score_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, vp, sz, i, szp]
     L.lm_seq_score_u8.argtypes = [vp, vp, vp, sz, sz, sz, sz, vp, sz, i, szp]
     L.lm_seq_score_argmax_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, i, hitp, cwp, f32p]
+    L.lm_seq_score_argmax_f32_launch.argtypes = [vp, vp, vp, sz, sz, sz, sz, i]
+    L.lm_seq_score_argmax_f32_finish.argtypes = [vp, i, i, hitp, cwp, f32p]
     L.lm_seq_score_threshold_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, C.c_float, hitp, sz, szp]
     L.lm_seq_score_argmax_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, hitp]
     L.lm_argmax_merge.argtypes = [cwp, sz, vp, C.c_float, C.c_uint64, i, hitp]

@@ -37,6 +37,7 @@ struct lm_ctx {
   DevBuf d_in, d_out, d_table, d_table2, d_small, d_hits;  // device scratch, grown on demand
   int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
   int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
+  int opt_reserve_sms = 0;                // LM_OPT_RESERVE_SMS: SMs left free for concurrent (NCCL) kernels
   size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
   uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
   // the last matrix uploaded to d_table / d_table2 and the last filter plan: a
@@ -44,6 +45,16 @@ struct lm_ctx {
   // host-side set-up once
   std::vector<uint8_t> table_key, table8_key, plan_key;
   PrunePlan plan_cache;
+  // in-flight fused argmax calls (launch / finish split, 2 slots): result blocks
+  // live at d_small + slot * 1024 and are copied to pinned host memory
+  struct Slot {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    void* h = nullptr;  // pinned SmallBlock
+    int state = 0;      // 0 idle, 1 in flight, 2 in flight but empty (LM_EMPTY)
+    size_t n_rows = 0;
+    bool pruned = false;
+    int r = 0;
+  } slots[2];
   void* h_pin = nullptr;                          // pinned host staging
   size_t h_pin_bytes = 0;
 };
@@ -257,7 +268,8 @@ int limits_ok(int alphabet, size_t m) {
 // already uploaded to ctx->d_table
 int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* seq, size_t avail_rows,
               size_t m, size_t row_begin, size_t row_end, void* d_out, size_t out_stride,
-              float thr_f32, uint8_t thr_u8, lm_hit* d_hits, size_t cap, bool standalone = true) {
+              float thr_f32, uint8_t thr_u8, lm_hit* d_hits, size_t cap, bool standalone = true,
+              size_t small_off = 0) {
   ScoreArgs a;
   a.seq = seq;
   a.avail_rows = avail_rows;
@@ -269,7 +281,7 @@ int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* se
   a.n_motifs = 1;
   a.out = d_out;
   a.out_stride = out_stride;
-  uint8_t* small = (uint8_t*)ctx->d_small.p;
+  uint8_t* small = (uint8_t*)ctx->d_small.p + small_off;
   a.colkeys = (unsigned long long*)small;
   a.first_cell = (uint32_t*)(small + 256);
   a.count = (unsigned long long*)(small + 264);
@@ -281,7 +293,7 @@ int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* se
     ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = ctx->stats[3] = 0;
     timer_begin(ctx);
   }
-  LM_TRY(launch_score(alphabet, mode, is_u8, a, ctx->sm_count, ctx->stream));
+  LM_TRY(launch_score(alphabet, mode, is_u8, a, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
   if (standalone) timer_end(ctx);
   ctx->launches += 1;
   return LM_OK;
@@ -421,6 +433,12 @@ int lm_ctx_create_on_stream(int device, void* cuda_stream, lm_ctx** out) {
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
   int s = ensure(ctx, ctx->d_small, SMALL_BYTES);
   if (s < 0) { lm_ctx_destroy(ctx); return s; }
+  for (auto& sl : ctx->slots) {
+    if ((e = cudaEventCreate(&sl.ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&sl.ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaHostAlloc(&sl.h, 512, cudaHostAllocDefault)) != cudaSuccess) return bail(e, "cudaHostAlloc");
+  }
   *out = ctx;
   return LM_OK;
 }
@@ -434,6 +452,12 @@ void lm_ctx_destroy(lm_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits})
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (auto& sl : ctx->slots) {
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.h) cudaFreeHost(sl.h);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -456,6 +480,10 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
     ctx->opt_prune = value;
     return LM_OK;
   }
+  if (option == LM_OPT_RESERVE_SMS && value >= 0 && value < 64) {
+    ctx->opt_reserve_sms = value;
+    return LM_OK;
+  }
   if (option == LM_OPT_FILTER_ROWS && value >= 0 && value <= 16) {
     ctx->opt_filter_rows = value;
     return LM_OK;
@@ -474,7 +502,8 @@ int lm_ctx_last_stats(const lm_ctx* ctx, uint64_t out[4]) {
 }
 
 float lm_ctx_last_kernel_ms(const lm_ctx* ctx) {
-  if (!ctx || !ctx->timed) return 0.f;
+  if (!ctx) return 0.f;
+  if (!ctx->timed) return ctx->last_ms;  // set by the last *_finish
   lm_ctx* c = const_cast<lm_ctx*>(ctx);
   if (cudaEventSynchronize(c->ev1) != cudaSuccess) return 0.f;
   float ms = 0.f;
@@ -926,15 +955,17 @@ int lm_seq_score_u8(lm_ctx* ctx, const lm_seq* seq, const uint8_t* dm, size_t m,
   return seq_score(ctx, seq, true, dm, m, dm_stride, row_begin, row_end, out, out_stride, out_is_device, out_rows);
 }
 
-int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
-                            size_t row_begin, size_t row_end, int rule, lm_hit* best, lm_colwin* per_column,
-                            float* first_cell) {
+int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m,
+                                   size_t pssm_stride, size_t row_begin, size_t row_end, int slot) {
   LM_CHECK(bind(ctx));
-  if (!seq || !pssm || !best || pssm_stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
+  if (!seq || !pssm || slot < 0 || slot > 1 || pssm_stride < (size_t)alphabet_k(seq->alphabet))
+    return LM_ERR_INVALID_ARG;
   if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
-  if (per_column) std::memset(per_column, 0, 32 * sizeof(lm_colwin));
+  lm_ctx::Slot& sl = ctx->slots[slot];
+  if (sl.state != 0) return LM_ERR_INVALID_ARG;  // previous launch on this slot not finished
   int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
-  if (st != LM_OK) return st;
+  if (st < 0) return st;
+  if (st == LM_EMPTY) { sl.state = 2; return LM_OK; }
   LM_CHECK(limits_ok(seq->alphabet, m));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
   const size_t n_rows = row_end - row_begin;
@@ -944,15 +975,16 @@ int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, s
     plan = cached_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
+  if (plan.ok) LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
+  const size_t off = (size_t)slot * 1024;
+  uint8_t* small = (uint8_t*)ctx->d_small.p + off;
+  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+  LM_TRY(cudaEventRecord(sl.ev0, ctx->stream));
   if (plan.ok) {
     // 1. exact scan of the first rows seeds the per-column winners (= the running maximum)
     // 2. filter + exact recheck over the rest, raising the maximum as it goes
-    LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
-    uint8_t* small = (uint8_t*)ctx->d_small.p;
-    LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
-    timer_begin(ctx);
     LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin,
-                       row_begin + ctx->opt_boot_rows, nullptr, 0, 0.f, 0, nullptr, 0, false));
+                       row_begin + ctx->opt_boot_rows, nullptr, 0, 0.f, 0, nullptr, 0, false, off));
     PruneArgs pa;
     pa.seq = seq->data;
     pa.avail_rows = seq->alloc_rows;
@@ -964,20 +996,55 @@ int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, s
     pa.plan = plan;
     pa.colkeys = (unsigned long long*)small;
     pa.stats = (unsigned long long*)(small + 272);
-    LM_TRY(launch_prune(false, pa, ctx->sm_count, ctx->stream));
-    timer_end(ctx);
+    LM_TRY(launch_prune(false, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
     ctx->launches += 1;
   } else {
     LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin, row_end,
-                       nullptr, 0, 0.f, 0, nullptr, 0));
+                       nullptr, 0, 0.f, 0, nullptr, 0, false, off));
   }
-  ColKeys ck;
-  LM_CHECK(fetch_colkeys(ctx, &ck, plan.ok ? &plan : nullptr));
+  LM_TRY(cudaEventRecord(sl.ev1, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(sl.h, small, sizeof(SmallBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaEventRecord(sl.done, ctx->stream));
+  sl.state = 1;
+  sl.n_rows = n_rows;
+  sl.pruned = plan.ok;
+  sl.r = plan.r;
+  return LM_OK;
+}
+
+int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best, lm_colwin* per_column,
+                                   float* first_cell) {
+  LM_CHECK(bind(ctx));
+  if (!best || slot < 0 || slot > 1) return LM_ERR_INVALID_ARG;
+  lm_ctx::Slot& sl = ctx->slots[slot];
+  if (per_column) std::memset(per_column, 0, 32 * sizeof(lm_colwin));
+  if (sl.state == 0) return LM_ERR_INVALID_ARG;
+  if (sl.state == 2) { sl.state = 0; return LM_EMPTY; }
+  sl.state = 0;
+  LM_TRY(cudaEventSynchronize(sl.done));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) { ctx->last_ms = ms; ctx->timed = false; }
+  const SmallBlock* sb = (const SmallBlock*)sl.h;
+  ctx->stats[0] = sl.pruned ? sb->stats[0] : 0;
+  ctx->stats[1] = sl.pruned ? sb->stats[1] : 0;
+  ctx->stats[2] = sl.pruned ? 1 : 0;
+  ctx->stats[3] = sl.pruned ? (uint64_t)sl.r : 0;
   lm_colwin cw[32];
-  decode_colwins(ck.keys, false, cw);
+  decode_colwins(sb->ck.keys, false, cw);
   if (per_column) std::memcpy(per_column, cw, sizeof(cw));
-  if (first_cell) *first_cell = bits_to_score(ck.first_cell, false);
-  return apply_rule(cw, bits_to_score(ck.first_cell, false), rule, false, row_end - row_begin, 0, best);
+  const float fc = bits_to_score(sb->ck.first_cell, false);
+  if (first_cell) *first_cell = fc;
+  return apply_rule(cw, fc, rule, false, sl.n_rows, 0, best);
+}
+
+int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
+                            size_t row_begin, size_t row_end, int rule, lm_hit* best, lm_colwin* per_column,
+                            float* first_cell) {
+  if (!best) return LM_ERR_INVALID_ARG;
+  if (ctx && ctx->slots[0].state != 0) return LM_ERR_INVALID_ARG;  // slot 0 is busy with an async call
+  int st = lm_seq_score_argmax_f32_launch(ctx, seq, pssm, m, pssm_stride, row_begin, row_end, 0);
+  if (st < 0) return st;
+  return lm_seq_score_argmax_f32_finish(ctx, 0, rule, best, per_column, first_cell);
 }
 
 int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
@@ -1016,7 +1083,7 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
     pa.count = (unsigned long long*)(small + 264);
     pa.stats = (unsigned long long*)(small + 272);
     timer_begin(ctx);
-    LM_TRY(launch_prune(true, pa, ctx->sm_count, ctx->stream));
+    LM_TRY(launch_prune(true, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
     timer_end(ctx);
     ctx->launches += 1;
     LM_CHECK(fetch_stats(ctx, plan));

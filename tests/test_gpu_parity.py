@@ -348,3 +348,25 @@ def test_kernels_actually_launched(dna):
     before = dna.kernel_launches
     dna.encode("ACGT")
     assert dna.kernel_launches == before + 1
+
+
+def test_launch_finish_pipeline(lm, dna, jaspar):
+    """lm_seq_score_argmax_f32_launch / _finish: two scans in flight return what
+    the one-shot call returns."""
+    n = 30_000_003
+    seq = dna.sequence_synthetic(n, 29)
+    pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in jaspar["motifs"][:6]] + [O.pssm_from_counts(O.DNA, jaspar["rest"], 0.1)]
+    want = [seq.score_argmax(p, with_columns=True) for p in pssms]
+    dna.set_reserve_sms(1)
+    got = []
+    seq.score_argmax_launch(pssms[0], slot=0)
+    for k in range(len(pssms)):
+        if k + 1 < len(pssms):
+            seq.score_argmax_launch(pssms[k + 1], slot=(k + 1) & 1)
+        got.append(seq.score_argmax_finish(slot=k & 1, with_columns=True))
+    dna.set_reserve_sms(0)
+    for w, g in zip(want, got):
+        assert {k: w[k] for k in ("row", "col", "position", "score", "first_cell")} == \
+               {k: g[k] for k in ("row", "col", "position", "score", "first_cell")}
+    with pytest.raises(lm.LightmotifError):
+        seq.score_argmax_finish(slot=1)  # nothing in flight
