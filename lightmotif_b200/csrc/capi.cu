@@ -299,15 +299,17 @@ int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* se
   return LM_OK;
 }
 
-// f32 table [m][8] (A,C,T,G,N,0,0,0) for the exact recheck of the pruned scan
+// f32 table [m_pad][8] (A,C,T,G,N,0,0,0) for the exact recheck of the pruned scan
 int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
   std::vector<uint8_t> key = matrix_key(3, LM_DNA, pssm, m, stride, 4);
   if (key == ctx->table8_key && ctx->d_table2.p) return LM_OK;
   ctx->table8_key = key;
-  const size_t bytes = m * 8 * 4;
+  const size_t m_pad = (m + 3) & ~(size_t)3;  // rows >= m are +0.0 (the recheck loop is unrolled by 4)
+  const size_t bytes = m_pad * 8 * 4;
   LM_CHECK(ensure_pinned(ctx, bytes));
   LM_CHECK(ensure(ctx, ctx->d_table2, bytes));
   float* h = (float*)ctx->h_pin;
+  std::memset(h, 0, bytes);
   for (size_t j = 0; j < m; ++j)
     for (int a = 0; a < 8; ++a) h[j * 8 + a] = a < 5 ? pssm[j * stride + a] : 0.f;
   LM_TRY(cudaMemcpyAsync(ctx->d_table2.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -1,20 +1,24 @@
 // prune.cu -- exact filter + recheck scan (DNA), see prune.cuh.
 //
-// Kernel (one CTA = 8 warps, tile = 672 striped rows x 32 columns = 21 504
-// positions, staged from HBM with one bulk-TMA copy, double-buffered):
+// Kernel.  Every WARP is autonomous: it pulls chunks of consecutive warp tiles
+// (4 * PL = 84 striped rows x 32 columns = 2688 positions) from a global
+// counter, stages each tile (+ halo) from HBM into its own double-buffered
+// shared-memory slot with one bulk-TMA copy (own mbarriers), filters it,
+// rechecks its own candidates.  There is no CTA-wide barrier in steady state.
 //
 //  filter   lane = (column quad q = lane & 7, row group g = lane >> 3); a thread
 //           walks PL (21) consecutive rows of its 4 columns.  One LDS.32 per row
 //           yields 4 symbols (4 adjacent columns = 4 independent positions);
-//           3 ALU ops turn them into a PRMT selector that is reused by all R
+//           IMAD + SHF turn them into a PRMT selector that is reused by all R
 //           filter rows:   acc = bias + sum_k PRMT(table[k], selector[i + k])
-//           (byte lanes, no carries across lanes by construction).  A
-//           position passes iff bit 7 of its byte is set, i.e. iff its integer
-//           upper bound reaches the current threshold.
-//  recheck  passing positions go to a shared-memory queue; after the filter
-//           pass the CTA rescans them EXACTLY (sequential f32 sum over all M
-//           rows in the reference's order, from the tile already in shared
-//           memory) and records those that really reach the threshold
+//           (byte lanes, no carries across lanes by construction; the adds are
+//           issued as IMADs so that they run on the FMA pipe beside the PRMTs
+//           on the ALU pipe).  A position passes iff bit 7 of its byte is set,
+//           i.e. iff its integer upper bound reaches the current threshold.
+//  recheck  passing positions go to the warp's shared-memory queue; after the
+//           filter pass the warp rescans them EXACTLY (sequential f32 sum over
+//           all M rows in the reference's order, from the tile already in
+//           shared memory) and records those that really reach the threshold
 //           (atomicMax on the per-column winner keys / hit list append).
 //  fallback a tile whose queue overflows (low-complexity sequence, very low
 //           threshold) is rescored exactly position by position.
@@ -32,8 +36,15 @@ namespace lm {
 
 namespace {
 
-constexpr int PW = 8;
-constexpr int PT = PW * 32;
+constexpr int PW = 8;                   // consumer (filter) warps per CTA
+constexpr int PT = (PW + 1) * 32;       // + one producer warp
+#ifndef LM_PRUNE_EXP
+#define LM_PRUNE_EXP 0
+#endif
+#ifndef LM_PRUNE_NSTAGE
+#define LM_PRUNE_NSTAGE 3
+#endif
+constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 #ifndef LM_PRUNE_PL
 #define LM_PRUNE_PL 21
 #endif
@@ -43,39 +54,49 @@ constexpr int PT = PW * 32;
 constexpr int PL = LM_PRUNE_PL;        // rows per thread per tile (odd => conflict-free LDS)
 constexpr int WARP_ROWS = 4 * PL;
 constexpr int PTILE_ROWS = PW * WARP_ROWS;
-constexpr int QCAP = 2048;
+constexpr int QCAP = 64;                // queue entries (quads) per warp and tile; more => exact fallback
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
 struct PSmem {
-  uint32_t raw_off, raw_bytes, queue_off, table_off, misc_off, total;
+  uint32_t table_off, ctl_off, queue_off, raw_off, raw_bytes, total;
+};
+// pipeline control block: full[s] (TMA landed + descriptor valid) / empty[s] (all consumer warps done)
+struct Ctl {
+  uint64_t full[NSTAGE], empty[NSTAGE];
+  struct { unsigned long long tile; uint32_t bias4; float thr; } desc[NSTAGE];
 };
 __host__ __device__ inline PSmem psmem(int m) {
   PSmem s;
   uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);
-  s.raw_off = 0;
-  s.raw_bytes = tt * 32;
-  s.queue_off = 2 * s.raw_bytes;
-  s.table_off = s.queue_off + QCAP * 4;
-  s.misc_off = s.table_off + (uint32_t)m * 8 * 4;
-  s.total = s.misc_off + 64;
+  s.table_off = 0;
+  s.ctl_off = ((uint32_t)((m + 3) & ~3) * 8 * 4 + 127) & ~127u;
+  s.queue_off = (s.ctl_off + (uint32_t)sizeof(Ctl) + 127) & ~127u;
+  s.raw_off = s.queue_off + PW * QCAP * 4;
+  s.raw_bytes = (tt * 32 + 127) & ~127u;
+  s.total = s.raw_off + NSTAGE * s.raw_bytes;
   return s;
 }
-
-struct Misc {
-  uint64_t bars[2];
-  unsigned long long next_tile[2];  // dynamically scheduled tile staged in each buffer
-  uint32_t qcount[2];               // double-buffered queue length (saves one barrier per tile)
-  uint32_t bias4;
-  float thr;
-  uint32_t thr_key;                 // threshold key the bias was computed for
-  uint32_t pad;
-};
 
 // raw PRMT (the __byte_perm intrinsic masks the selector with 0x7777 first)
 __device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
   return d;
+}
+
+// acc + p as `p * one + acc`: an IMAD on the (otherwise idle) FMA pipe instead of an IADD3 on the
+// ALU pipe that the PRMT look-ups saturate.  `one` is a kernel parameter so ptxas cannot fold it.
+#ifndef LM_PRUNE_IMAD
+#define LM_PRUNE_IMAD 1
+#endif
+__device__ __forceinline__ uint32_t add_fma_pipe(uint32_t p, uint32_t one, uint32_t acc) {
+#if LM_PRUNE_IMAD
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(p), "r"(one), "r"(acc));
+  return d;
+#else
+  return acc + p;
+#endif
 }
 
 // PRMT selector of a quad (4 symbols, one per byte, each <= 7):
@@ -104,101 +125,68 @@ __device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel
   }
 }
 
-// exact sequential f32 score of the window starting at (row_in_tile, col)
-__device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* tab, int m,
+// exact sequential f32 score of the window starting at (row_in_tile, col).  The table is padded
+// to a multiple of 4 rows with +0.0 (x + 0.0 == x: the chain starts at +0.0 and never yields -0.0).
+__device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* tab, int m_pad,
                                              uint32_t row_in_tile, uint32_t col) {
   float s = 0.0f;
   const uint8_t* p = rawb + row_in_tile * 32 + col;
-  for (int j = 0; j < m; ++j) s = __fadd_rn(s, tab[j * 8 + p[j * 32]]);
+  for (int j = 0; j < m_pad; j += 4) {
+    const uint32_t s0 = p[0], s1 = p[32], s2 = p[64], s3 = p[96];
+    const float w0 = tab[s0], w1 = tab[8 + s1], w2 = tab[16 + s2], w3 = tab[24 + s3];
+    s = __fadd_rn(s, w0);
+    s = __fadd_rn(s, w1);
+    s = __fadd_rn(s, w2);
+    s = __fadd_rn(s, w3);
+    p += 128;
+    tab += 32;
+  }
   return s;
 }
-
-#ifdef LM_PRUNE_DEBUG
-__device__ unsigned long long g_dbg[2048][4];
-#endif
 
 template <int R, bool THR>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const PSmem S = psmem(a.plan.m);
-  uint8_t* raw = smem + S.raw_off;
-  uint32_t* queue = reinterpret_cast<uint32_t*>(smem + S.queue_off);
-  float* tab = reinterpret_cast<float*>(smem + S.table_off);
-  Misc* misc = reinterpret_cast<Misc*>(smem + S.misc_off);
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane & 7, g = lane >> 3;
   const int m = a.plan.m;
-  const uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);
+  const PSmem S = psmem(m);
+  const uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);  // rows staged per tile (tile + halo)
+  float* tab = reinterpret_cast<float*>(smem + S.table_off);
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + S.ctl_off);
+  uint8_t* raw = smem + S.raw_off;
 
   if (tid == 0) {
-    mbar_init(&misc->bars[0], 1);
-    mbar_init(&misc->bars[1], 1);
-    mbar_fence_init();
-    misc->qcount[0] = misc->qcount[1] = 0;
-  }
-  for (int i = tid; i < m * 8; i += PT) tab[i] = a.table[i];
-  __syncthreads();
-
-  auto stage = [&](uint64_t tile, int buf) {
-    uint64_t r0 = a.row_first + tile * PTILE_ROWS;
-    uint64_t avail = a.avail_rows > r0 ? a.avail_rows - r0 : 0;
-    uint32_t nrows = avail < tt ? (uint32_t)avail : tt;
-    fence_proxy_async();
-    mbar_expect_tx(&misc->bars[buf], nrows * 32);
-    if (nrows) tma_load_1d(raw + (size_t)buf * S.raw_bytes, a.seq + r0 * 32, nrows * 32, &misc->bars[buf]);
-  };
-
-  // filter tables in per-thread registers.  They are bounced through shared
-  // memory on purpose: PRMT cannot take its table operand from a uniform
-  // register, and ptxas would otherwise keep the (uniform) kernel-parameter
-  // values in URs and re-materialise them with a UR->R move before every look-up.
-  uint32_t tlo[R], thi[R];
-  {
-    uint32_t* tq = queue;  // the queue is unused until the first filter pass
-    if (tid < R) { tq[tid] = a.plan.tab_lo[tid]; tq[16 + tid] = a.plan.tab_hi[tid]; }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&tq[k]);
-      thi[k] = *reinterpret_cast<volatile uint32_t*>(&tq[16 + k]);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], PW);
     }
-    __syncthreads();
+    mbar_fence_init();
   }
+  const int m_pad = (m + 3) & ~3;
+  for (int i = tid; i < m_pad * 8; i += PT) tab[i] = a.table[i];  // [m_pad][8], rows >= m are +0.0
+  __syncthreads();  // the only CTA-wide barrier: from here on warps meet through mbarriers only
 
-  // dynamic tile scheduling: CTAs pull tiles from a global counter so that all of them finish
-  // together (with a static split the first-launched CTA of an SM runs ahead and the SM ends with
-  // too few warps); the tile for iteration it+1 is claimed when its prefetch is issued
-  auto claim = [&]() -> unsigned long long { return atomicAdd(&a.stats[2], 1ull); };
-  if (tid == 0) {
-    unsigned long long t0 = claim();
-    misc->next_tile[0] = t0;
-    misc->thr_key = 0xffffffffu;
-    if (t0 < num_tiles) stage(t0, 0);
-  }
-  unsigned long long n_cand = 0, n_over = 0;
-#ifdef LM_PRUNE_DEBUG
-  unsigned long long dbg_t0 = 0, dbg_g0 = 0;
-  if (tid == 0) { dbg_t0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_g0)); }
-#endif
-  // threshold key prefetched one tile ahead (L2 latency off the critical path; stale is safe)
-  uint32_t sk_next = 0;
-  if (!THR && warp == 0) sk_next = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
-  __syncthreads();
-
-  uint32_t it = 0;
-  for (;; ++it) {
-    const int buf = it & 1;
-    const uint64_t tile = misc->next_tile[buf];
-    if (tile >= num_tiles) break;
-    // ---- current threshold -> byte bias (recomputed only when the threshold moved)
-    if (warp == 0) {
-      uint32_t sk = sk_next;
+  if (warp == PW) {
+    // ===================== producer warp: claims tiles, stages them with bulk TMA, publishes the
+    // threshold each tile is to be filtered at.  Tiles are claimed one at a time from a global
+    // counter, so the CTAs of the whole grid sweep the sequence as one dense window.
+    uint32_t thr_key = 0xffffffffu, bias4 = 0;
+    float thr = THR ? a.thr : -INFINITY;
+    for (uint32_t it = 0;; ++it) {
+      const int s = it % NSTAGE;
+      // claim the tile and fetch the running maximum first: both round trips overlap the wait
+      unsigned long long tile = 0;
+      if (lane == 0) tile = atomicAdd(&a.stats[2], 1ull);
+      uint32_t sk = 0;
+      if (!THR) sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
       if (!THR) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
       }
-      if (lane == 0 && (THR ? it == 0 : sk != misc->thr_key)) {
+      if (it >= NSTAGE) mbar_wait_hint(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, 4000);
+      // ---- current threshold -> byte bias (recomputed only when the threshold moved)
+      if (THR ? it == 0 : sk != thr_key) {
         const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
         // sum_q >= qthr is implied by fp32score >= t (see header); -1 guards the division
         double need = ((double)t - a.plan.eps - a.plan.c0) / a.plan.delta;
@@ -210,50 +198,110 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           qthr = qthr < 1 ? 1 : (qthr > 128 ? 128 : qthr);
           bias = 128 - qthr;
         }
-        misc->bias4 = (uint32_t)bias * 0x01010101u;
-        misc->thr = t;
-        misc->thr_key = sk;
+        bias4 = (uint32_t)bias * 0x01010101u;
+        thr = t;
+        thr_key = sk;
       }
-    }
-    mbar_wait(&misc->bars[buf], (it >> 1) & 1);
-    const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;
-    uint8_t* rawb = raw + (size_t)buf * S.raw_bytes;
-    {
-      uint64_t avail = a.avail_rows > tile_row0 ? a.avail_rows - tile_row0 : 0;
-      if (avail < tt) {
-        uint32_t w0 = (uint32_t)avail * 8, w1 = tt * 8;
-        uint32_t fill = a.pad_sym * 0x01010101u;
-        for (uint32_t w = w0 + tid; w < w1; w += PT) reinterpret_cast<uint32_t*>(rawb)[w] = fill;
+      if (lane == 0) {
+        ctl->desc[s].tile = tile;
+        ctl->desc[s].bias4 = bias4;
+        ctl->desc[s].thr = thr;
+        if (tile < num_tiles) {
+#if LM_PRUNE_EXP == 2  // experiment: no DRAM traffic (every tile re-reads the first few tiles from L2)
+          uint64_t r0 = a.row_first + (tile & 3) * PTILE_ROWS;
+#else
+          uint64_t r0 = a.row_first + tile * PTILE_ROWS;
+#endif
+          uint64_t avail = a.avail_rows > r0 ? a.avail_rows - r0 : 0;
+          uint32_t nrows = avail < tt ? (uint32_t)avail : tt;
+          fence_proxy_async();
+          mbar_expect_tx(&ctl->full[s], nrows * 32);
+          if (nrows) tma_load_1d(raw + (size_t)s * S.raw_bytes, a.seq + r0 * 32, nrows * 32, &ctl->full[s]);
+        } else {
+          mbar_arrive(&ctl->full[s]);  // end marker: consumers read desc.tile >= num_tiles and leave
+        }
       }
+      if (tile >= num_tiles) break;
     }
-    __syncthreads();  // (A) tile + bias visible; every thread is done with the previous tile
-    {
-      // claim + prefetch the next tile into the other buffer (free since barrier A)
-      if (tid == 0) {
-        unsigned long long nt = claim();
-        misc->next_tile[buf ^ 1] = nt;
-        if (nt < num_tiles) stage(nt, buf ^ 1);
-      }
-      if (!THR && warp == 0) sk_next = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
-    }
-    const uint32_t bias4 = misc->bias4;
-    const float thr = misc->thr;
-    const uint64_t left = a.row_end - tile_row0;
-    const uint32_t rows_valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
-    uint32_t* qcount = &misc->qcount[buf];
+    return;
+  }
 
-    // ---- filter
+  // ===================== consumer warps: warp w filters rows [w * WARP_ROWS, (w + 1) * WARP_ROWS) of
+  // every tile and rechecks its own candidates
+  const int q = lane & 7, g = lane >> 3;
+  uint32_t* queue = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;
+  const uint32_t lanemask_lt = (1u << lane) - 1u;
+
+  // filter tables in per-thread registers.  They are bounced through shared
+  // memory on purpose: PRMT cannot take its table operand from a uniform
+  // register, and ptxas would otherwise keep the (uniform) kernel-parameter
+  // values in URs and re-materialise them with a UR->R move before every look-up.
+  uint32_t tlo[R], thi[R];
+  {
+    if (lane < R) { queue[lane] = a.plan.tab_lo[lane]; queue[16 + lane] = a.plan.tab_hi[lane]; }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&queue[k]);
+      thi[k] = *reinterpret_cast<volatile uint32_t*>(&queue[16 + k]);
+    }
+    __syncwarp();
+  }
+  const uint32_t one = a.one;
+  unsigned long long n_cand = 0, n_over = 0;
+
+  for (uint32_t it = 0;; ++it) {
+    const int s = it % NSTAGE;
+    mbar_wait_hint(&ctl->full[s], (it / NSTAGE) & 1, 2000);
+    const uint64_t tile = ctl->desc[s].tile;
+    if (tile >= num_tiles) break;
+    const uint32_t bias4 = ctl->desc[s].bias4;
+    const float thr = ctl->desc[s].thr;
+    const uint32_t wrow0 = warp * WARP_ROWS;                       // this warp's first row in the tile
+    const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;
+    uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
     {
-      const uint32_t row_base = warp * WARP_ROWS + g * PL;
+      // rows past the readable extent (end of the sequence only): default symbol.  Every warp fills
+      // the rows IT reads; overlapping halo rows get the same value from both neighbours.
+      uint64_t avail = a.avail_rows > tile_row0 ? a.avail_rows - tile_row0 : 0;
+      const uint32_t wend = wrow0 + WARP_ROWS + ((m + 3) & ~3);
+      if (avail < wend) {
+        uint32_t w0 = (avail > wrow0 ? (uint32_t)avail : wrow0) * 8, w1 = wend * 8;
+        uint32_t fill = a.pad_sym * 0x01010101u;
+        for (uint32_t w = w0 + lane; w < w1; w += 32) reinterpret_cast<uint32_t*>(rawb)[w] = fill;
+        __syncwarp();
+      }
+    }
+    const uint64_t left = a.row_end - tile_row0;  // > 0 for every claimed tile
+    const uint32_t tile_valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
+    const uint32_t rows_valid = tile_valid > wrow0 ? min(tile_valid - wrow0, (uint32_t)WARP_ROWS) : 0;
+
+#if LM_PRUNE_EXP == 1  // experiment: stream the tiles, no filtering
+    if (rows_valid && bias4 == 0x12345678u) {
+#else
+    if (rows_valid) {
+#endif
+      // ---- filter
+      const uint32_t row_base = wrow0 + g * PL;
       const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb) + (row_base + a.plan.j0) * 8 + q;
       uint32_t sel[PL + R - 1];
 #pragma unroll
       for (int i = 0; i < R - 1; ++i) sel[i] = make_sel(rp[i * 8]);
-      auto push = [&](uint32_t acc, int i) {
-        const uint32_t msk = acc & 0x80808080u;
-        if (msk) {  // queue the quad: row, column quad, which of its 4 byte lanes passed
-          const uint32_t idx = atomicAdd(qcount, 1u);
-          if (idx < QCAP) queue[idx] = ((row_base + i) << 7) | (q << 4) | (((msk >> 7) * 0x10204080u) >> 28);
+      // Candidates are appended to the warp's queue with a ballot (the queue length lives in a
+      // warp-uniform register: no shared-memory atomics, and the branch is warp-uniform).  One
+      // entry = a PAIR of consecutive quad rows: first row, column quad, 2 x 4 byte-lane flags.
+      uint32_t nq = 0;
+      auto push2 = [&](uint32_t lo, uint32_t hi, int i0) {
+        const bool mine = ((lo | hi) & 0x80808080u) != 0;  // one LOP3 with a predicate result
+        if (__any_sync(0xffffffffu, mine)) {
+          const uint32_t votes = __ballot_sync(0xffffffffu, mine);
+          if (mine) {
+            const uint32_t mlo = lo & 0x80808080u, mhi = hi & 0x80808080u;
+            const uint32_t slot = nq + __popc(votes & lanemask_lt);
+            const uint32_t flags = (((mlo >> 7) * 0x10204080u) >> 28) | ((((mhi >> 7) * 0x10204080u) >> 28) << 4);
+            if (slot < QCAP) queue[slot] = ((row_base + i0) << 11) | (q << 8) | flags;
+          }
+          nq += __popc(votes);
         }
       };
       uint32_t prev = 0;
@@ -262,52 +310,39 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         sel[i + R - 1] = make_sel(rp[(i + R - 1) * 8]);
         uint32_t acc = bias4;
 #pragma unroll
-        for (int k = 0; k < R; ++k) acc += prmt_raw(tlo[k], thi[k], sel[i + k]);
-        // one test per PAIR of quads ((a | b) & mask is a single LOP3); the rare hit re-tests each
-        if (i & 1) {
-          if ((prev | acc) & 0x80808080u) { push(prev, i - 1); push(acc, i); }
-        } else if (i == PL - 1) {
-          if (acc & 0x80808080u) push(acc, i);
-        }
+        for (int k = 0; k < R; ++k) acc = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + k]), one, acc);
+        if (i & 1) push2(prev, acc, i - 1);          // one test per PAIR of quad rows
+        else if (i == PL - 1) push2(acc, 0u, i);
         prev = acc;
       }
-    }
-    __syncthreads();  // (B) queue complete
+      __syncwarp();  // queue complete
 
-    // ---- exact recheck of the candidates (or of the whole tile on overflow)
-    const uint32_t nq = *qcount;
-    if (tid == 0) misc->qcount[buf ^ 1] = 0;  // nobody touches the other counter until the next barrier A
-    if (nq <= QCAP) {
-      for (uint32_t k = tid; k < nq * 4; k += PT) {
-        const uint32_t code = queue[k >> 2], b = k & 3;
-        if (!((code >> b) & 1u)) continue;
-        const uint32_t row = code >> 7, col = ((code >> 4) & 7u) * 4 + LANE_COL[b];
-        if (row >= rows_valid) continue;
-        float s = exact_score(rawb, tab, m, row, col);
-        if (s >= thr) record<THR>(a, s, (uint32_t)(tile_row0 + row - a.row_begin), col);
+      // ---- exact recheck of the candidates (or of the warp's whole slice on overflow)
+      if (nq) {
+        if (nq <= QCAP) {
+          for (uint32_t k = lane; k < nq * 8; k += 32) {
+            const uint32_t code = queue[k >> 3], b = k & 7;
+            if (!((code >> b) & 1u)) continue;
+            const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
+            if (row >= tile_valid) continue;
+            float sc = exact_score(rawb, tab, m_pad, row, col);
+            if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
+          }
+          n_cand += nq;
+        } else {
+          for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
+            uint32_t row = wrow0 + (p >> 5), col = p & 31;
+            float sc = exact_score(rawb, tab, m_pad, row, col);
+            if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
+          }
+          n_over += 1;
+        }
       }
-      if (tid == 0) n_cand += nq;
-    } else {
-      for (uint32_t p = tid; p < rows_valid * 32; p += PT) {
-        uint32_t row = p >> 5, col = p & 31;
-        float s = exact_score(rawb, tab, m, row, col);
-        if (s >= thr) record<THR>(a, s, (uint32_t)(tile_row0 + row - a.row_begin), col);
-      }
-      if (tid == 0) n_over += 1;
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->empty[s]);  // this warp is done with the stage
   }
-#ifdef LM_PRUNE_DEBUG
-  if (tid == 0 && blockIdx.x < 2048) {
-    unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    unsigned long long g1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
-    g_dbg[blockIdx.x][0] = clock64() - dbg_t0;
-    g_dbg[blockIdx.x][1] = n_cand;
-    g_dbg[blockIdx.x][2] = smid | ((unsigned long long)it << 32);
-    g_dbg[blockIdx.x][3] = dbg_g0 | 0;  // start time (ns)
-    (void)g1;
-  }
-#endif
-  if (tid == 0 && a.stats) {
+  if (lane == 0 && a.stats) {
     if (n_cand) atomicAdd(&a.stats[0], n_cand);
     if (n_over) atomicAdd(&a.stats[1], n_over);
   }
@@ -512,12 +547,6 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
   return best;
 }
 
-#ifdef LM_PRUNE_DEBUG
-extern "C" void lm_debug_dump(unsigned long long* out, int n) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, g_dbg, sizeof(unsigned long long) * 4 * n);
-}
-#endif
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream) {
   return threshold_mode ? launch_r<true>(a, sm_count, stream) : launch_r<false>(a, sm_count, stream);

@@ -49,7 +49,8 @@ struct PruneArgs {
   uint64_t row_first = 0;        // first row THIS launch scans (>= row_begin; rows before were bootstrapped)
   uint64_t row_end = 0;
   uint8_t pad_sym = 4;
-  const float* table = nullptr;  // device: [m][8] f32 (A,C,T,G,N,0,0,0)
+  uint32_t one = 1;              // opaque multiplier: `acc = p * one + acc` keeps the byte-lane adds on the FMA pipe (IMAD)
+  const float* table = nullptr;  // device: [m rounded up to 4][8] f32 (A,C,T,G,N,0,0,0), pad rows +0.0
   PrunePlan plan;
   // argmax mode: colkeys[32] holds the running per-column winners (read for the
   // dynamic threshold, updated with atomicMax)
