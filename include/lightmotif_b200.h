@@ -116,16 +116,20 @@ float lm_ctx_last_kernel_ms(const lm_ctx *ctx);
 /* rows scored exactly first to seed the running maximum of a filtered argmax
  * scan (default 262144) */
 #define LM_OPT_BOOT_ROWS 2
-/* force the number of filter rows (4, 6, 8, 10, 12 or 16; 0 = planner decides) */
+/* force the number of filter look-ups per position (single-row mode: 4, 6, 8,
+ * 10, 12 or 16; paired mode: 3, 4, 5, 6 or 8; 0 = planner decides) */
 #define LM_OPT_FILTER_ROWS 3
 /* leave this many SMs out of the persistent scoring grids so that a concurrent
  * small kernel (the NCCL all-gather of the previous scan's winners) can run
  * next to a scan (default 0) */
 #define LM_OPT_RESERVE_SMS 4
+/* filter look-up flavour: 0 = planner decides, 1 = one motif row per look-up,
+ * 2 = paired (one row exactly + one class bit of the next row per look-up) */
+#define LM_OPT_FILTER_MODE 5
 int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
 /* statistics of the most recent fused call: out[0] = cells rechecked exactly,
  * out[1] = tiles that fell back to exact scoring, out[2] = 1 if the filter
- * path ran, out[3] = filter rows used */
+ * path ran, out[3] = filter look-ups per position | (paired mode << 8) */
 int lm_ctx_last_stats(const lm_ctx *ctx, uint64_t out[4]);
 
 /* --------------------------------------------- host-buffer trait mirrors */

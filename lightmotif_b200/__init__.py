@@ -283,6 +283,10 @@ class Pipeline:
         """LM_OPT_FILTER_ROWS: force the filter depth (0 = planner decides)."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 3, int(r)))
 
+    def set_filter_mode(self, mode):
+        """LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single-row look-ups, 2 = paired look-ups."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 5, int(mode)))
+
     def set_reserve_sms(self, n):
         """LM_OPT_RESERVE_SMS: SMs left free for concurrent kernels (NCCL)."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 4, int(n)))
@@ -296,7 +300,7 @@ class Pipeline:
         out = (C.c_uint64 * 4)()
         self._check(capi.lib().lm_ctx_last_stats(self._ctx, C.byref(out)))
         return {"rechecked": int(out[0]), "overflow_tiles": int(out[1]), "pruned": bool(out[2]),
-                "filter_rows": int(out[3])}
+                "filter_rows": int(out[3]) & 0xff, "paired": bool(int(out[3]) >> 8)}
 
     # ---- Encode ---------------------------------------------------------
     @staticmethod

@@ -37,6 +37,7 @@ struct lm_ctx {
   DevBuf d_in, d_out, d_table, d_table2, d_small, d_hits;  // device scratch, grown on demand
   int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
   int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
+  int opt_filter_mode = 0;                // LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single rows, 2 = paired rows
   int opt_reserve_sms = 0;                // LM_OPT_RESERVE_SMS: SMs left free for concurrent (NCCL) kernels
   size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
   uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
@@ -322,12 +323,13 @@ int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
 PrunePlan cached_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, bool argmax_mode, double t,
                       double npos) {
   std::vector<uint8_t> key = matrix_key(argmax_mode ? 4 : 5, LM_DNA, pssm, m, stride, 4);
-  double extra[3] = {argmax_mode ? 0.0 : t, npos, (double)ctx->opt_filter_rows};
+  double extra[4] = {argmax_mode ? 0.0 : t, npos, (double)ctx->opt_filter_rows, (double)ctx->opt_filter_mode};
   key.insert(key.end(), (const uint8_t*)extra, (const uint8_t*)extra + sizeof(extra));
   if (key == ctx->plan_key) return ctx->plan_cache;
   PrunePlan plan = argmax_mode
-      ? plan_prune(pssm, m, stride, estimate_max_score(pssm, m, stride, npos), true, npos, ctx->opt_filter_rows)
-      : plan_prune(pssm, m, stride, t, false, npos, ctx->opt_filter_rows);
+      ? plan_prune(pssm, m, stride, estimate_max_score(pssm, m, stride, npos), true, npos, ctx->opt_filter_rows,
+                   ctx->opt_filter_mode)
+      : plan_prune(pssm, m, stride, t, false, npos, ctx->opt_filter_rows, ctx->opt_filter_mode);
   ctx->plan_key.swap(key);
   ctx->plan_cache = plan;
   return plan;
@@ -340,7 +342,7 @@ int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
   ctx->stats[0] = st[0];
   ctx->stats[1] = st[1];
   ctx->stats[2] = 1;
-  ctx->stats[3] = (uint64_t)plan.r;
+  ctx->stats[3] = (uint64_t)plan.r | ((uint64_t)plan.pair << 8);
   return LM_OK;
 }
 
@@ -361,7 +363,7 @@ int fetch_colkeys(lm_ctx* ctx, ColKeys* out, const PrunePlan* plan = nullptr) {
     ctx->stats[0] = sb.stats[0];
     ctx->stats[1] = sb.stats[1];
     ctx->stats[2] = 1;
-    ctx->stats[3] = (uint64_t)plan->r;
+    ctx->stats[3] = (uint64_t)plan->r | ((uint64_t)plan->pair << 8);
   }
   return LM_OK;
 }
@@ -488,6 +490,10 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
   }
   if (option == LM_OPT_FILTER_ROWS && value >= 0 && value <= 16) {
     ctx->opt_filter_rows = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_FILTER_MODE && value >= 0 && value <= 2) {
+    ctx->opt_filter_mode = value;
     return LM_OK;
   }
   if (option == LM_OPT_BOOT_ROWS && value >= 1) {
@@ -1010,7 +1016,7 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
   sl.state = 1;
   sl.n_rows = n_rows;
   sl.pruned = plan.ok;
-  sl.r = plan.r;
+  sl.r = plan.r | (plan.pair << 8);
   return LM_OK;
 }
 

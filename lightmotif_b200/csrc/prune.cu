@@ -1,27 +1,32 @@
 // prune.cu -- exact filter + recheck scan (DNA), see prune.cuh.
 //
-// Kernel.  Every WARP is autonomous: it pulls chunks of consecutive warp tiles
-// (4 * PL = 84 striped rows x 32 columns = 2688 positions) from a global
-// counter, stages each tile (+ halo) from HBM into its own double-buffered
-// shared-memory slot with one bulk-TMA copy (own mbarriers), filters it,
-// rechecks its own candidates.  There is no CTA-wide barrier in steady state.
+// Kernel.  One CTA = 8 consumer (filter) warps + 1 producer warp, persistent.
 //
-//  filter   lane = (column quad q = lane & 7, row group g = lane >> 3); a thread
-//           walks PL (21) consecutive rows of its 4 columns.  One LDS.32 per row
-//           yields 4 symbols (4 adjacent columns = 4 independent positions);
-//           IMAD + SHF turn them into a PRMT selector that is reused by all R
-//           filter rows:   acc = bias + sum_k PRMT(table[k], selector[i + k])
-//           (byte lanes, no carries across lanes by construction; the adds are
-//           issued as IMADs so that they run on the FMA pipe beside the PRMTs
-//           on the ALU pipe).  A position passes iff bit 7 of its byte is set,
-//           i.e. iff its integer upper bound reaches the current threshold.
-//  recheck  passing positions go to the warp's shared-memory queue; after the
-//           filter pass the warp rescans them EXACTLY (sequential f32 sum over
-//           all M rows in the reference's order, from the tile already in
-//           shared memory) and records those that really reach the threshold
+//  producer claims tiles (8 x 4 x PL = 864 striped rows x 32 columns = 27 648 positions) one at a
+//           time from a global counter -- so the whole grid sweeps the sequence as one dense
+//           window --, stages each tile (+ halo) from HBM with ONE bulk-TMA copy into a ring of
+//           NSTAGE shared-memory buffers (full[s] / empty[s] mbarriers), and publishes with each
+//           tile the threshold it is to be filtered at (the running maximum, read from L2).
+//           There is no CTA-wide barrier in steady state.
+//  filter   consumer warp w owns rows [w * 4 PL, (w + 1) * 4 PL) of the tile; lane = (column quad
+//           q = lane & 7, row group g = lane >> 3); a thread walks PL consecutive rows of its 4
+//           columns.  One LDS.32 per row yields 4 symbols (4 adjacent columns = 4 independent
+//           positions); one IDP.2A packs them into a PRMT selector that is reused by every
+//           look-up touching that row:   acc = bias + sum_k PRMT(table[k], selector[i + k])
+//           (byte lanes, no carries across lanes by construction; the adds are issued as IMADs
+//           so that they run on the FMA pipe beside the PRMTs on the ALU pipe).  A position
+//           passes iff bit 7 of its byte is set, i.e. iff its integer upper bound reaches the
+//           current threshold.  In PAIRED mode a look-up covers TWO motif rows: the 8-entry PRMT
+//           table is indexed by the symbol of the first row and one class bit of the second
+//           row's symbol (entry = w1(s) + max over the class of w2), a valid upper bound that
+//           costs one extra IMAD + LOP3 per sequence row.
+//  recheck  passing positions go to the warp's shared-memory queue (ballot-compacted, the queue
+//           length lives in a warp-uniform register); after the filter pass the warp rescans
+//           them EXACTLY (sequential f32 sum over all M rows in the reference's order, from the
+//           tile still in shared memory) and records those that really reach the threshold
 //           (atomicMax on the per-column winner keys / hit list append).
-//  fallback a tile whose queue overflows (low-complexity sequence, very low
-//           threshold) is rescored exactly position by position.
+//  fallback a warp whose queue overflows (low-complexity sequence, very low threshold) rescans
+//           its slice of the tile exactly, position by position.
 //
 // The bound:  UB(p) = c0 + delta * sum_q(p) >= real-valued score(p), and the
 // fp32 sequential sum differs from the real sum by at most eps, so
@@ -42,11 +47,11 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #define LM_PRUNE_EXP 0
 #endif
 #ifndef LM_PRUNE_NSTAGE
-#define LM_PRUNE_NSTAGE 3
+#define LM_PRUNE_NSTAGE 2
 #endif
 constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 #ifndef LM_PRUNE_PL
-#define LM_PRUNE_PL 21
+#define LM_PRUNE_PL 27
 #endif
 #ifndef LM_PRUNE_MINBLOCKS
 #define LM_PRUNE_MINBLOCKS 3
@@ -54,7 +59,7 @@ constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 constexpr int PL = LM_PRUNE_PL;        // rows per thread per tile (odd => conflict-free LDS)
 constexpr int WARP_ROWS = 4 * PL;
 constexpr int PTILE_ROWS = PW * WARP_ROWS;
-constexpr int QCAP = 64;                // queue entries (quads) per warp and tile; more => exact fallback
+constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
 struct PSmem {
@@ -99,13 +104,16 @@ __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t p, uint32_t one, uint3
 #endif
 }
 
-// PRMT selector of a quad (4 symbols, one per byte, each <= 7):
-//   x * 0x00100001 = x + (x << 20) puts s2@16, s0@20, s3@24, s1@28 (no overlaps),
-// so the top half holds the four symbols as nibbles in the order (2, 0, 3, 1):
-// one IMAD (FMA pipe) + one shift instead of three ALU ops.  Byte lane b of
-// every look-up therefore belongs to column LANE_COL[b] of the quad.
-__device__ __forceinline__ uint32_t make_sel(uint32_t x) { return (x * 0x00100001u) >> 16; }
-__device__ __constant__ const uint8_t LANE_COL[4] = {2, 0, 3, 1};
+// PRMT selector of a quad (4 symbols, one per byte, each <= 7): a single IDP.2A (FMA pipe)
+//   dp2a.lo(x, {1, 16}) = (s0 + 256 s1) * 1 + (s2 + 256 s3) * 16 = s0 | s2 << 4 | s1 << 8 | s3 << 12
+// packs the four symbols as nibbles in the order (0, 2, 1, 3).  Byte lane b of every look-up
+// therefore belongs to column LANE_COL[b] of the quad.
+__device__ __forceinline__ uint32_t make_sel(uint32_t x) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0x00001001u), "r"(0u));
+  return d;
+}
+__device__ __constant__ const uint8_t LANE_COL[4] = {0, 2, 1, 3};
 
 template <bool THR>
 __device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel_row, uint32_t col) {
@@ -144,7 +152,7 @@ __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* t
   return s;
 }
 
-template <int R, bool THR>
+template <int R, bool PAIR, bool THR>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,9 +292,30 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       // ---- filter
       const uint32_t row_base = wrow0 + g * PL;
       const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb) + (row_base + a.plan.j0) * 8 + q;
-      uint32_t sel[PL + R - 1];
+      // selector window.  Single mode: look-up k of position i uses row i + k.  Paired mode:
+      // look-up k uses the COMBINED selector of rows (i + 2k, i + 2k + 1): symbol of the first
+      // row | one class bit of the second row << 2 (8-entry table = 4 symbols x 2 classes).
+      constexpr int W = PAIR ? 2 * R : R;        // motif rows spanned by the filter
+      constexpr int STEP = PAIR ? 2 : 1;
+      constexpr int NSEL = PAIR ? PL + W - 2 : PL + W - 1;
+      uint32_t sel[NSEL];
+      uint32_t raw_prev = 0;
+      const uint32_t pair_mul = a.plan.pair_mul;
+      auto combine = [&](uint32_t lo_row, uint32_t hi_row) {  // IMAD (FMA pipe) + LOP3
+        return lo_row | ((hi_row * pair_mul) & 0x4444u);
+      };
+      if (PAIR) {
+        raw_prev = make_sel(rp[0]);
 #pragma unroll
-      for (int i = 0; i < R - 1; ++i) sel[i] = make_sel(rp[i * 8]);
+        for (int i = 0; i < W - 2; ++i) {
+          const uint32_t nx = make_sel(rp[(i + 1) * 8]);
+          sel[i] = combine(raw_prev, nx);
+          raw_prev = nx;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < W - 1; ++i) sel[i] = make_sel(rp[i * 8]);
+      }
       // Candidates are appended to the warp's queue with a ballot (the queue length lives in a
       // warp-uniform register: no shared-memory atomics, and the branch is warp-uniform).  One
       // entry = a PAIR of consecutive quad rows: first row, column quad, 2 x 4 byte-lane flags.
@@ -307,10 +336,16 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       uint32_t prev = 0;
 #pragma unroll
       for (int i = 0; i < PL; ++i) {
-        sel[i + R - 1] = make_sel(rp[(i + R - 1) * 8]);
+        if (PAIR) {
+          const uint32_t nx = make_sel(rp[(i + W - 1) * 8]);
+          sel[i + W - 2] = combine(raw_prev, nx);
+          raw_prev = nx;
+        } else {
+          sel[i + W - 1] = make_sel(rp[(i + W - 1) * 8]);
+        }
         uint32_t acc = bias4;
 #pragma unroll
-        for (int k = 0; k < R; ++k) acc = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + k]), one, acc);
+        for (int k = 0; k < R; ++k) acc = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc);
         if (i & 1) push2(prev, acc, i - 1);          // one test per PAIR of quad rows
         else if (i == PL - 1) push2(acc, 0u, i);
         prev = acc;
@@ -354,14 +389,25 @@ cudaError_t launch_r(const PruneArgs& a, int sm_count, cudaStream_t stream) {
   const uint64_t num_tiles = (a.row_end - a.row_first + PTILE_ROWS - 1) / PTILE_ROWS;
   const PSmem S = psmem(a.plan.m);
   void (*kern)(const PruneArgs, uint64_t) = nullptr;
-  switch (a.plan.r) {
-    case 4: kern = prune_kernel<4, THR>; break;
-    case 6: kern = prune_kernel<6, THR>; break;
-    case 8: kern = prune_kernel<8, THR>; break;
-    case 10: kern = prune_kernel<10, THR>; break;
-    case 12: kern = prune_kernel<12, THR>; break;
-    case 16: kern = prune_kernel<16, THR>; break;
-    default: return cudaErrorInvalidValue;
+  if (a.plan.pair) {
+    switch (a.plan.r) {
+      case 3: kern = prune_kernel<3, true, THR>; break;
+      case 4: kern = prune_kernel<4, true, THR>; break;
+      case 5: kern = prune_kernel<5, true, THR>; break;
+      case 6: kern = prune_kernel<6, true, THR>; break;
+      case 8: kern = prune_kernel<8, true, THR>; break;
+      default: return cudaErrorInvalidValue;
+    }
+  } else {
+    switch (a.plan.r) {
+      case 4: kern = prune_kernel<4, false, THR>; break;
+      case 6: kern = prune_kernel<6, false, THR>; break;
+      case 8: kern = prune_kernel<8, false, THR>; break;
+      case 10: kern = prune_kernel<10, false, THR>; break;
+      case 12: kern = prune_kernel<12, false, THR>; break;
+      case 16: kern = prune_kernel<16, false, THR>; break;
+      default: return cudaErrorInvalidValue;
+    }
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
   if (e != cudaSuccess) return e;
@@ -446,8 +492,38 @@ double estimate_max_score(const float* pssm, size_t m, size_t stride, double n_p
   return maxsum - span * res;
 }
 
+namespace {
+
+// One PRMT look-up of the filter: up to 8 table entries with their real-valued contents and
+// their probabilities under a uniform ACGT background.
+struct Unit {
+  double v[8];
+  double prob[8];
+  int n;
+};
+
+// Modelled cost (issue slots per quad row = 128 positions of one warp instruction stream) of a
+// filter with `r` look-ups spanning `w` motif rows whose per-position pass rate is `pass`.
+// Calibrated on B200 (profiles/README.md).
+double filter_cost(int r, int w, bool pair, double pass) {
+  const double halo = (double)(PL + w - 1) / PL;
+  const double core = 2.0 * r + (pair ? 4.0 : 2.0) * halo + 2.5;
+  // slow path of the pair test: taken when any of the 64 quads of a warp pair has a candidate
+  const double p_quad = std::min(1.0, 4.0 * pass);
+  const double push = 12.5 * (1.0 - std::pow(1.0 - p_quad, 64.0));
+  // exact recheck, per warp tile (WARP_ROWS * 32 positions): one pass of ~130 slots per 32 flags
+  const double lambda = pass * WARP_ROWS * 32.0;
+  const double recheck = (130.0 * (1.0 - std::exp(-lambda)) + 130.0 * lambda * 8.0 / 32.0) / PL;
+  // queue overflow => the warp rescans its slice exactly (~350 slots per quad row)
+  const double overflow = lambda > QCAP / 4.0 ? 350.0 : 0.0;
+  return core + push + recheck + overflow;
+}
+constexpr double EXACT_COST = 350.0;  // exact-everywhere kernel, same unit
+
+}  // namespace
+
 PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, bool t_is_estimate,
-                     double n_positions, int force_r) {
+                     double n_positions, int force_r, int force_mode) {
   PrunePlan best;
   Rows r;
   if (m < 4 || m > PRUNE_MAX_M || !load_rows(pssm, m, stride, r)) return best;
@@ -463,90 +539,136 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
     max_total += r.rowmax[j];
   }
   const double eps = 2.0 * (double)m * std::ldexp(1.0, -24) * abs_sum + 1e-30;
-  static const int RS[] = {4, 6, 8, 10, 12, 16};
+  static const int RS_SINGLE[] = {4, 6, 8, 10, 12, 16};
+  static const int RS_PAIR[] = {3, 4, 5, 6, 8};
   static const double CS[] = {4.0, 6.0, 8.0, 12.0, CLAMP_FLOOR};
   double best_cost = 1e300;
-  // cost model calibrated on B200 (profiles/README.md): per position, a filter of R rows costs
-  // ~(1.5 R + 15.6) / 4 issue slots, a queued candidate ~870 (divergent recheck), exact scoring ~55
-  const double EXACT_COST = 55.0, RECHECK_COST = 870.0;
-  for (int R : RS) {
-    if (R > (int)m || (force_r && R != force_r)) continue;
-    for (int j0 = 0; j0 + R <= (int)m; ++j0) {
-      double restmax = max_total;
-      for (int k = 0; k < R; ++k) restmax -= r.rowmax[j0 + k];
-      for (double C : CS) {
-        // clamped weights, per-row base, step
-        double wc[16][5], base[16], range_sum = 0, base_sum = 0;
-        for (int k = 0; k < R; ++k) {
-          const double mx = r.rowmax[j0 + k];
-          double mn = INFINITY;
+
+  auto consider = [&](bool pair, int R, int j0, uint32_t mul, double C) {
+    const int W = pair ? 2 * R : R;  // rows [j0, j0 + W) are covered; rows >= m do not exist
+    Unit u[16];
+    double restmax = max_total;
+    for (int k = 0; k < R; ++k) {
+      Unit& U = u[k];
+      if (!pair) {
+        const int row = j0 + k;
+        restmax -= r.rowmax[row];
+        U.n = 5;  // A, C, T, G, N (N: probability 0, but its entry must still bound its weight)
+        for (int a = 0; a < 5; ++a) { U.v[a] = r.w[row * 5 + a]; U.prob[a] = a < 4 ? 0.25 : 0.0; }
+      } else {
+        const int rf = j0 + 2 * k, rh = rf + 1;  // full row, half (class-bit) row
+        restmax -= r.rowmax[rf];
+        // half row: best weight within each class of the second symbol.  class(s) = bit 2 of
+        // s * mul: mul = 2 -> {T, G}, mul = 4 -> {C, G}; N (4) is always class 0.
+        double hmax[2] = {0.0, 0.0}, hall = 0.0;
+        if (rh < (int)m) {
+          restmax -= r.rowmax[rh];
+          hmax[0] = hmax[1] = -INFINITY;
           for (int a = 0; a < 5; ++a) {
-            wc[k][a] = std::max(r.w[(j0 + k) * 5 + a], mx - C);
-            mn = std::min(mn, wc[k][a]);
+            const int cls = ((a * mul) >> 2) & 1;
+            hmax[cls] = std::max(hmax[cls], r.w[rh * 5 + a]);
           }
-          base[k] = mn;
-          base_sum += mn;
-          range_sum += mx - mn;
+          hall = std::max(hmax[0], hmax[1]);
         }
-        if (!(range_sum > 0)) continue;
-        const double delta = range_sum / (127.0 - R);
-        int q[16][5], smax = 0;
-        for (int k = 0; k < R; ++k) {
-          int mxq = 0;
-          for (int a = 0; a < 5; ++a) {
-            q[k][a] = (int)std::ceil((wc[k][a] - base[k]) / delta - 1e-9);
-            if (q[k][a] < 0) q[k][a] = 0;
-            // make sure the bound holds despite the 1e-9 slack
-            while (base[k] + q[k][a] * delta < wc[k][a]) q[k][a]++;
-            mxq = std::max(mxq, q[k][a]);
-          }
-          smax += mxq;
-        }
-        if (smax > 127) continue;
-        const double c0 = base_sum + restmax;
-        // pass rate under uniform ACGT at t_plan
-        double need = (t_plan - eps - c0) / delta;
-        int qthr = need > 1.0 ? (int)std::ceil(need) - 1 : 0;
-        double pass;
-        if (qthr <= 0) pass = 1.0;
-        else if (qthr > smax) pass = 0.0;
-        else {
-          double d[128] = {0}, nd[128];
-          d[0] = 1.0;
-          for (int k = 0; k < R; ++k) {
-            std::fill(nd, nd + 128, 0.0);
-            for (int a = 0; a < 4; ++a)
-              for (int i = 0; i + q[k][a] < 128; ++i) nd[i + q[k][a]] += 0.25 * d[i];
-            std::copy(nd, nd + 128, d);
-          }
-          pass = 0;
-          for (int i = qthr; i < 128; ++i) pass += d[i];
-        }
-        const double cost = (1.5 * R + 15.6) / 4.0 + pass * RECHECK_COST;
-        if (cost < best_cost) {
-          best_cost = cost;
-          best.m = (int)m;
-          best.r = R;
-          best.j0 = j0;
-          best.smax = smax;
-          best.c0 = c0;
-          best.delta = delta;
-          best.eps = eps;
-          best.est_pass_rate = pass;
-          for (int k = 0; k < 16; ++k) best.tab_lo[k] = best.tab_hi[k] = 0;
-          for (int k = 0; k < R; ++k) {
-            best.tab_lo[k] = (uint32_t)q[k][0] | ((uint32_t)q[k][1] << 8) | ((uint32_t)q[k][2] << 16) |
-                             ((uint32_t)q[k][3] << 24);
-            best.tab_hi[k] = (uint32_t)q[k][4];
-          }
-        }
+        U.n = 8;  // entry = s | class << 2
+        for (int b = 0; b < 2; ++b)
+          for (int a = 0; a < 4; ++a) { U.v[a + 4 * b] = r.w[rf * 5 + a] + hmax[b]; U.prob[a + 4 * b] = 0.125; }
+        // N in the full row encodes as nibble 4 | class << 2 = entry (A, class 1) whatever the
+        // second symbol is: that entry must also bound  w(N) + any second-row weight
+        U.v[4] = std::max(U.v[4], r.w[rf * 5 + 4] + hall);
       }
+    }
+    // clamp from below, per-unit base, quantisation step
+    double base[16], range_sum = 0, base_sum = 0;
+    for (int k = 0; k < R; ++k) {
+      double mx = -INFINITY, mn = INFINITY;
+      for (int e = 0; e < u[k].n; ++e) mx = std::max(mx, u[k].v[e]);
+      if (!std::isfinite(mx)) return;
+      for (int e = 0; e < u[k].n; ++e) {
+        u[k].v[e] = std::max(u[k].v[e], mx - C * (pair ? 1.5 : 1.0));
+        mn = std::min(mn, u[k].v[e]);
+      }
+      base[k] = mn;
+      base_sum += mn;
+      range_sum += mx - mn;
+    }
+    if (!(range_sum > 0)) return;
+    const double delta = range_sum / (127.0 - R);
+    int q[16][8], smax = 0;
+    for (int k = 0; k < R; ++k) {
+      int mxq = 0;
+      for (int e = 0; e < u[k].n; ++e) {
+        q[k][e] = (int)std::ceil((u[k].v[e] - base[k]) / delta - 1e-9);
+        if (q[k][e] < 0) q[k][e] = 0;
+        while (base[k] + q[k][e] * delta < u[k].v[e]) q[k][e]++;  // the bound must hold despite the slack
+        mxq = std::max(mxq, q[k][e]);
+      }
+      for (int e = u[k].n; e < 8; ++e) q[k][e] = 0;
+      smax += mxq;
+    }
+    if (smax > 127) return;
+    const double c0 = base_sum + restmax;
+    // pass rate under uniform ACGT at t_plan
+    double need = (t_plan - eps - c0) / delta;
+    int qthr = need > 1.0 ? (int)std::ceil(need) - 1 : 0;
+    double pass;
+    if (qthr <= 0) pass = 1.0;
+    else if (qthr > smax) pass = 0.0;
+    else {
+      double d[128] = {0}, nd[128];
+      d[0] = 1.0;
+      for (int k = 0; k < R; ++k) {
+        std::fill(nd, nd + 128, 0.0);
+        for (int e = 0; e < u[k].n; ++e)
+          if (u[k].prob[e] > 0)
+            for (int i = 0; i + q[k][e] < 128; ++i) nd[i + q[k][e]] += u[k].prob[e] * d[i];
+        std::copy(nd, nd + 128, d);
+      }
+      pass = 0;
+      for (int i = qthr; i < 128; ++i) pass += d[i];
+    }
+    const double cost = filter_cost(R, std::min<int>(W, (int)m - j0), pair, pass);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best.m = (int)m;
+      best.r = R;
+      best.pair = pair ? 1 : 0;
+      best.pair_mul = mul;
+      best.j0 = j0;
+      best.smax = smax;
+      best.c0 = c0;
+      best.delta = delta;
+      best.eps = eps;
+      best.est_pass_rate = pass;
+      best.est_cost = cost;
+      for (int k = 0; k < 16; ++k) best.tab_lo[k] = best.tab_hi[k] = 0;
+      for (int k = 0; k < R; ++k) {
+        best.tab_lo[k] = (uint32_t)q[k][0] | ((uint32_t)q[k][1] << 8) | ((uint32_t)q[k][2] << 16) |
+                         ((uint32_t)q[k][3] << 24);
+        best.tab_hi[k] = (uint32_t)q[k][4] | ((uint32_t)q[k][5] << 8) | ((uint32_t)q[k][6] << 16) |
+                         ((uint32_t)q[k][7] << 24);
+      }
+    }
+  };
+
+  if (force_mode != 2) {
+    for (int R : RS_SINGLE) {
+      if (R > (int)m || (force_r && R != force_r)) continue;
+      for (int j0 = 0; j0 + R <= (int)m; ++j0)
+        for (double C : CS) consider(false, R, j0, 0, C);
+    }
+  }
+  if (force_mode != 1) {
+    for (int R : RS_PAIR) {
+      if (2 * R - 1 > (int)m || (force_r && R != force_r)) continue;  // the last half row may be missing
+      for (int j0 = 0; j0 + 2 * R - 1 <= (int)m; ++j0)
+        for (uint32_t mul : {2u, 4u})
+          for (double C : CS) consider(true, R, j0, mul, C);
     }
   }
   best.ok = best_cost < EXACT_COST && best.r > 0;
   return best;
 }
-
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream) {
   return threshold_mode ? launch_r<true>(a, sm_count, stream) : launch_r<false>(a, sm_count, stream);

@@ -19,14 +19,19 @@ constexpr int PRUNE_MAX_M = 256;
 // Host-built plan for one DNA PSSM.
 struct PrunePlan {
   int m = 0;          // motif rows
-  int r = 0;          // filter rows (contiguous block [j0, j0 + r)), one of 4,6,8,10,12,16
+  int r = 0;          // PRMT look-ups per position.  Single mode (pair == 0): look-up k covers motif row
+                      // j0 + k, r in {4,6,8,10,12,16}.  Paired mode: look-up k covers row j0 + 2k exactly
+                      // and row j0 + 2k + 1 through one class bit of its symbol, r in {3,4,5,6,8}.
+  int pair = 0;
+  uint32_t pair_mul = 2;  // paired mode: class(s) = bit 2 of s * pair_mul (2: {T,G}, 4: {C,G})
   int j0 = 0;
-  uint32_t tab_lo[16];  // per filter row: bytes = q[j][A,C,T,G]
-  uint32_t tab_hi[16];  // per filter row: byte 0 = q[j][N], bytes 1..3 = 0
+  uint32_t tab_lo[16];  // per look-up: table entries 0..3 (single: q[A,C,T,G]; paired: class 0)
+  uint32_t tab_hi[16];  // per look-up: table entries 4..7 (single: q[N],0,0,0;   paired: class 1)
   int smax = 0;         // max attainable sum of q over the filter rows (<= 127)
   // UB(p) = c0 + delta * sum_q(p)  >=  real-valued score(p);  fp32 score <= real + eps
   double c0 = 0, delta = 1, eps = 0;
   double est_pass_rate = 1.0;  // under a uniform background at the planning threshold
+  double est_cost = 0.0;       // modelled issue slots per quad row (128 positions)
   bool ok = false;
 };
 
@@ -35,8 +40,9 @@ struct PrunePlan {
 // threshold, or an estimate of the final maximum for argmax scans over
 // `n_positions` cells).  Returns plan.ok == false when pruning is not
 // expected to pay off (the caller then uses the exact-everywhere kernel).
+// `force_r` != 0 forces the number of look-ups, `force_mode` 1 = single rows only, 2 = paired only.
 PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, bool t_is_estimate,
-                     double n_positions, int force_r = 0);
+                     double n_positions, int force_r = 0, int force_mode = 0);
 
 // Score quantile helper used for argmax planning: the score t such that the
 // expected number of cells with score >= t among n uniform-random positions is ~1.

@@ -62,16 +62,23 @@ def make_sequence(rng, n, kind):
 
 
 def compare(pli, seq, pssm, thresholds):
+    """exact-everywhere (prune 0) vs the filter in both look-up flavours (single rows, paired rows)."""
     res = {}
-    for mode in (0, 2):
+    for key, mode, fmode in (("exact", 0, 0), ("single", 2, 1), ("paired", 2, 2)):
         pli.set_prune(mode)
-        res[mode] = {"argmax": {r: seq.score_argmax(pssm, rule=r) for r in (0, 1, 2)},
-                     "stats": pli.last_stats,
-                     "thr": {t: seq.score_threshold(pssm, t) for t in thresholds}}
-    for r in (0, 1, 2):
-        assert res[0]["argmax"][r] == res[2]["argmax"][r], (r, res[0]["argmax"][r], res[2]["argmax"][r])
-    for t in thresholds:
-        assert res[0]["thr"][t] == res[2]["thr"][t], t
+        pli.set_filter_mode(fmode)
+        res[key] = {"argmax": {r: seq.score_argmax(pssm, rule=r) for r in (0, 1, 2)},
+                    "stats": pli.last_stats,
+                    "thr": {t: seq.score_threshold(pssm, t) for t in thresholds}}
+    pli.set_filter_mode(0)
+    for key in ("single", "paired"):
+        for r in (0, 1, 2):
+            assert res["exact"]["argmax"][r] == res[key]["argmax"][r], (key, r, res["exact"]["argmax"][r], res[key]["argmax"][r])
+        for t in thresholds:
+            assert res["exact"]["thr"][t] == res[key]["thr"][t], (key, t)
+    if len(pssm) >= 8:  # both flavours have a plan for motifs this long
+        assert res["single"]["stats"]["pruned"] and not res["single"]["stats"]["paired"]
+        assert res["paired"]["stats"]["pruned"] and res["paired"]["stats"]["paired"]
     return res
 
 
@@ -95,11 +102,12 @@ def test_pruned_equals_exact(dna, m, pk, sk):
     # and against the CPU oracle on the materialised scores
     for r in (0, 1, 2):
         rr, cc = O.argmax(ref, r)
-        got = res[2]["argmax"][r]
+        got = res["paired"]["argmax"][r]
         assert (got["row"], got["col"]) == (rr, cc)
         assert np.float32(got["score"]).view(np.uint32) == ref[rr, cc].view(np.uint32)
     ro, co = O.threshold(ref, ts[0])
-    assert [(h["row"], h["col"]) for h in res[2]["thr"][ts[0]]] == list(zip(ro.tolist(), co.tolist()))
+    for key in ("single", "paired"):
+        assert [(h["row"], h["col"]) for h in res[key]["thr"][ts[0]]] == list(zip(ro.tolist(), co.tolist()))
 
 
 def test_pruned_actually_prunes_and_matches_on_rest(dna, jaspar):
@@ -147,8 +155,10 @@ def test_all_equal_sequence_ties(dna):
     dna.set_boot_rows(1024)
     dna.set_prune(0)
     ref = seq.score(pssm)
-    for r in (0, 1, 2):
-        dna.set_prune(2)
-        got = seq.score_argmax(pssm, rule=r)
-        rr, cc = O.argmax(ref, r)
-        assert (got["row"], got["col"]) == (rr, cc), r
+    for fmode in (1, 2):
+        dna.set_filter_mode(fmode)
+        for r in (0, 1, 2):
+            dna.set_prune(2)
+            got = seq.score_argmax(pssm, rule=r)
+            rr, cc = O.argmax(ref, r)
+            assert (got["row"], got["col"]) == (rr, cc), (fmode, r)

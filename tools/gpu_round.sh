@@ -14,5 +14,5 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-exact > $OUT/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:prune_kernel -s 2 -c 1 -f -o $OUT/prune_full_$TAG \
-    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-exact --bp-per-gpu 1000000000 > $OUT/ncu_full_$TAG.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-exact > $OUT/ncu_full_$TAG.log 2>&1
 ls -la $OUT

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--prune", type=int, default=1)
     ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--fmode", type=int, default=0)
+    ap.add_argument("--boot", type=int, default=0)
     ap.add_argument("--thr", type=float, default=18.0)
     a = ap.parse_args()
     z = np.load(Path(__file__).resolve().parent.parent / "tests/golden/jaspar2024.npz")
@@ -34,6 +36,9 @@ def main():
     pli = lm.Pipeline.cuda(lm.DNA)
     pli.set_prune(a.prune)
     pli.set_filter_rows(a.rows)
+    pli.set_filter_mode(a.fmode)
+    if a.boot:
+        pli.set_boot_rows(a.boot)
     seq = pli.sequence_synthetic(a.bp, a.m - 1)
     times = []
     res = None
