@@ -78,9 +78,32 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(const uint8_t* __re
 // Fused (encode +) stripe + wrap: writes rows [0, out_rows) of the striped
 // matrix of a sequence whose GLOBAL striped matrix has `rows` rows; the slab
 // starts at global row `row0`.  src holds symbols (FROM_ASCII = false) or raw
-// ASCII (true) of the whole sequence (n bytes).
-constexpr int ST_ROWS = 256;  // rows per CTA tile
+// ASCII (true) of the whole sequence (n bytes) and is 4-byte aligned.
+//
+// One CTA tile = ST_ROWS striped rows x 32 columns.  Column c of the tile is the
+// contiguous source range S'[c * rows + r .. + ST_ROWS): phase 1 streams the 32
+// ranges with fully coalesced 4-byte loads (a warp reads 128 contiguous bytes
+// per instruction, starting at the enclosing 4-byte boundary), encodes a word at
+// a time, and parks them in shared memory column-major; phase 2 re-aligns each
+// column with a funnel shift, transposes 4x4 byte blocks with PRMT and writes
+// 32-byte rows.  HBM-bound: 1 byte read + 1 byte written per symbol.
+#ifndef LM_ST_ROWS
+#define LM_ST_ROWS 512
+#endif
+constexpr int ST_ROWS = LM_ST_ROWS;        // rows per CTA tile
 constexpr int ST_THREADS = 256;
+constexpr int ST_COLW = ST_ROWS / 4 + 3;   // words per column in shared memory: odd => conflict-free
+
+// 4 ASCII bytes -> 4 DNA codes, fast path: (x >> 1) & 3 maps A, C, T, G to 0, 1, 2, 3; the word is
+// accepted iff rebuilding the letters from the codes gives the input back.  Returns false when any
+// byte needs the table (N, lower case, anything else).
+__device__ __forceinline__ bool dna_word_fast(uint32_t w, uint32_t& code) {
+  code = (w >> 1) & 0x03030303u;
+  uint32_t sel;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(sel) : "r"(code), "r"(0x00001001u), "r"(0u));  // nibbles c0 c2 c1 c3
+  const uint32_t letters = __byte_perm(0x47544341u /* "ACTG" */, 0u, sel);
+  return letters == __byte_perm(w, 0u, 0x3120);
+}
 
 template <bool FROM_ASCII>
 __global__ void __launch_bounds__(ST_THREADS) stripe_kernel(const uint8_t* __restrict__ src, uint64_t n,
@@ -89,41 +112,94 @@ __global__ void __launch_bounds__(ST_THREADS) stripe_kernel(const uint8_t* __res
                                                             int alphabet, uint8_t pad,
                                                             unsigned long long* first_bad) {
   __shared__ uint8_t lut[256];
-  __shared__ __align__(16) uint8_t tile[32][ST_ROWS + 4];  // [column][row], +4 keeps word alignment, shifts banks
+  __shared__ uint32_t tile[32][ST_COLW];  // [column][word]; column c starts `shift[c]` bytes into its first word
+  __shared__ uint32_t shift[32];
   if (FROM_ASCII) build_lut(lut, alphabet);
   unsigned long long bad = ~0ull;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t ntiles = (out_rows + ST_ROWS - 1) / ST_ROWS;
+  const uint32_t pad4 = pad * 0x01010101u;
+  const bool dna = alphabet == LM_DNA;
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
+  constexpr int NJ = (ST_COLW + 31) / 32, NC = 32 / (ST_THREADS / 32);
+  uint32_t raw[NC][NJ];
+
+  // All of a thread's loads for a tile (4 columns x 5 words) are issued before any is consumed: the
+  // bytes in flight, not the instruction rate, decide how much of the HBM bandwidth this kernel sees.
+  auto fetch = [&](uint64_t t) {
+    const uint64_t r0 = t * ST_ROWS;
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+      const int c = warp + ci * (ST_THREADS / 32);
+      const uint64_t w_first = ((uint64_t)c * rows + row0 + r0) >> 2;  // enclosing source word of the segment
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int wi = j * 32 + lane;
+        raw[ci][j] = (wi < ST_COLW && (w_first + wi) * 4 < n) ? __ldg(&src32[w_first + wi]) : pad4;
+      }
+    }
+  };
+
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t r0 = t * ST_ROWS;  // local row of the tile
-    // phase 1: 32 column segments of ST_ROWS consecutive symbols each
-    for (int c = warp; c < 32; c += ST_THREADS / 32) {
-      for (int k = lane; k < ST_ROWS; k += 32) {
-        uint64_t r = row0 + r0 + k;             // global striped row
-        uint64_t p = (uint64_t)c * rows + r;    // sequence index S'(c*rows + r)
-        uint8_t code = pad;
-        if (p < n && r0 + k < out_rows) {
-          uint8_t x = src[p];
+    fetch(t);
+    // ---- phase 1: encode the 32 column segments (ST_ROWS consecutive symbols each) into shared memory
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+      const int c = warp + ci * (ST_THREADS / 32);
+      const uint64_t p_first = (uint64_t)c * rows + row0 + r0;  // sequence index of the segment's first symbol
+      const uint64_t w_first = p_first >> 2;
+      if (lane == 0) shift[c] = (uint32_t)(p_first & 3);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int wi = j * 32 + lane;
+        if (wi >= ST_COLW) break;
+        const uint64_t p0 = (w_first + wi) * 4;  // sequence index of byte 0 of this word
+        const uint32_t w = raw[ci][j];
+        uint32_t out = pad4;
+        if (p0 < n) {
           if (FROM_ASCII) {
-            code = lut[x];
-            if (code == 0xFF) { bad = p < bad ? p : bad; code = pad; }
+            uint32_t code;
+            if (dna && p0 + 3 < n && dna_word_fast(w, code)) {
+              out = code;
+            } else {
+              out = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                uint32_t cde = pad;
+                if (p0 + b < n) {
+                  cde = lut[(w >> (8 * b)) & 0xFF];
+                  if (cde == 0xFF) {
+                    if (p0 + b < bad) bad = p0 + b;  // any invalid byte of the sequence may be reported: the minimum wins
+                    cde = pad;
+                  }
+                }
+                out |= cde << (8 * b);
+              }
+            }
+          } else if (p0 + 3 < n) {
+            out = w;
           } else {
-            code = x;
+            out = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) out |= (p0 + b < n ? (w >> (8 * b)) & 0xFFu : (uint32_t)pad) << (8 * b);
           }
         }
-        tile[c][k] = code;
+        tile[c][wi] = out;
       }
     }
     __syncthreads();
-    // phase 2: 4x4 byte transposes, 32-byte rows written as 8 x 4 bytes
+    // ---- phase 2: re-align, 4x4 byte transposes, 32-byte rows written as 8 x 4 bytes
     for (int blk = threadIdx.x; blk < (ST_ROWS / 4) * 8; blk += ST_THREADS) {
-      int cb = blk & 7, rb = blk >> 3;
-      uint32_t w0 = *reinterpret_cast<const uint32_t*>(&tile[4 * cb + 0][4 * rb]);
-      uint32_t w1 = *reinterpret_cast<const uint32_t*>(&tile[4 * cb + 1][4 * rb]);
-      uint32_t w2 = *reinterpret_cast<const uint32_t*>(&tile[4 * cb + 2][4 * rb]);
-      uint32_t w3 = *reinterpret_cast<const uint32_t*>(&tile[4 * cb + 3][4 * rb]);
-      uint32_t u = __byte_perm(w0, w1, 0x5140), v = __byte_perm(w2, w3, 0x5140);
-      uint32_t x = __byte_perm(w0, w1, 0x7362), y = __byte_perm(w2, w3, 0x7362);
+      const int cb = blk & 7, rb = blk >> 3;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 4 * cb + i;
+        w[i] = __funnelshift_r(tile[c][rb], tile[c][rb + 1], 8 * shift[c]);
+      }
+      uint32_t u = __byte_perm(w[0], w[1], 0x5140), v = __byte_perm(w[2], w[3], 0x5140);
+      uint32_t x = __byte_perm(w[0], w[1], 0x7362), y = __byte_perm(w[2], w[3], 0x7362);
       uint32_t o[4] = {__byte_perm(u, v, 0x5410), __byte_perm(u, v, 0x7632),
                        __byte_perm(x, y, 0x5410), __byte_perm(x, y, 0x7632)};
 #pragma unroll
@@ -207,7 +283,7 @@ cudaError_t launch_stripe(const uint8_t* src, bool from_ascii, uint64_t n, uint6
   if (out_rows == 0) return cudaSuccess;
   uint8_t pad = (uint8_t)(alphabet_k(alphabet) - 1);
   uint64_t ntiles = (out_rows + ST_ROWS - 1) / ST_ROWS;
-  unsigned grid = (unsigned)(ntiles < (uint64_t)sm_count * 4 ? ntiles : (uint64_t)sm_count * 4);
+  unsigned grid = (unsigned)(ntiles < (uint64_t)sm_count * 16 ? ntiles : (uint64_t)sm_count * 16);
   if (from_ascii)
     stripe_kernel<true><<<grid, ST_THREADS, 0, stream>>>(src, n, rows, row0, out_rows, dst, alphabet, pad, first_bad);
   else
