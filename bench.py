@@ -51,16 +51,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: an NVML
-    polling thread (the timed region can be a few tens of ms, too short for
-    `nvidia-smi -lms`), falling back to one nvidia-smi query."""
+    """SM clock and throttle reasons for the timed region.
+
+    * `sm_mhz` is measured ON THE DEVICE, every step: the scan kernel reads the SM cycle counter and
+      the global nanosecond timer at its start and end (lm_ctx_last_sm_clock_mhz), so it is the
+      clock the timed kernels actually ran at.
+    * throttle reasons (and an NVML clock reading for cross-checking) are sampled through NVML
+      immediately before the first and after the last timed step -- the GPU is hot from the warm-up
+      steps -- and, on a single GPU, also inline between steps.  NVML calls are kept out of the
+      multi-GPU timed region: each one stalls the NCCL-coupled pipeline of both ranks by ~4 ms on
+      these hosts (measured: 10 steps went from 1.25 to 2.57 ms/step with three inline queries; a
+      2 ms polling thread cost 40 %)."""
+
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop, self._thread, self._nvml = None, None, None
-
-    def start(self):
-        import threading
+        self.index, self.kernel_mhz, self.nvml_mhz, self.reasons, self.max_mhz, self._nvml = index, [], [], set(), None, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -69,40 +75,39 @@ class ClockSampler:
             self._nvml = (pynvml, h)
         except Exception:
             self._nvml = None
+
+    def sample_nvml(self):
+        if self._nvml is None:
             return
-        self._stop = threading.Event()
-        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        nv, h = self._nvml
+        try:
+            self.nvml_mhz.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self.BITS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
-        def poll():
-            nv, hh = self._nvml
-            while not self._stop.is_set():
-                try:
-                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(hh, nv.NVML_CLOCK_SM)))
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hh)
-                    for name, bit in bits.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    break
-                time.sleep(0.002)
+    def sample_kernel(self, mhz):
+        if mhz and mhz > 0:
+            self.kernel_mhz.append(float(mhz))
 
-        self._thread = threading.Thread(target=poll, daemon=True)
-        self._thread.start()
-
-    def stop(self):
-        if self._thread is not None:
-            self._stop.set()
-            self._thread.join(timeout=2)
-        if not self.samples:  # NVML unavailable: one nvidia-smi reading right after the region
+    def result(self):
+        if self.max_mhz is None:
             try:
                 out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
                 a, b = [float(x) for x in out.strip().split(",")]
-                self.samples, self.max_mhz = [a], b
+                self.nvml_mhz, self.max_mhz = [a], b
             except Exception:
-                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["unavailable"]}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+                pass
+        src = self.kernel_mhz or self.nvml_mhz
+        return {"sm_mhz": statistics.median(src) if src else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(src), "reasons": sorted(self.reasons),
+                "how": ("in-kernel cycle counter / global timer, one sample per timed step" if self.kernel_mhz
+                        else "NVML") + "; reasons via NVML just before / after the timed steps",
+                "nvml_sm_mhz": self.nvml_mhz}
 
 
 def cpu_baseline(pssm, threads=None, target_s=10.0, sample_bp=256_000_000):
@@ -184,7 +189,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("LM_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None) if "LM_NCCL_DEBUG" not in os.environ else os.environ.__setitem__("NCCL_DEBUG", os.environ["LM_NCCL_DEBUG"])  # NCCL_DEBUG prints its banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     per_gpu = args.bp_per_gpu
@@ -201,30 +206,35 @@ def run_ours(args):
     positions = (r1 - r0) * 32  # cells scored per step on this rank (1 byte each)
 
     xchg = lmdist.WinnerExchange(device=dev) if world > 1 else None
-    xstream = torch.cuda.Stream(device=dev) if world > 1 else None
-    if world > 1:
-        pli.set_reserve_sms(1)  # one SM stays free so the all-gather of scan k overlaps scan k+1
+    row_offsets = [rows_global * r // world for r in range(world)]
 
-    # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners.  Steps are
-    # software-pipelined one deep: scan k+1 is enqueued before the host finishes / exchanges scan k.
+    # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners: an NCCL
+    # all-gather of the 272-byte result block straight from HBM, enqueued on the scan's stream, and
+    # the tie-rule merge on the host.  Steps are software-pipelined one deep: scan k+1 is enqueued
+    # before the host waits for scan k.
     def launch(k):
         seq.score_argmax_launch(pssm, slot=k & 1)
+        if world > 1:
+            xchg.enqueue(pli.result_block_ptr(k & 1), slot=k & 1)
 
     def finish(k):
-        res = seq.score_argmax_finish(slot=k & 1, rule=lm.RULE_AVX2, with_columns="numpy")
+        res = seq.score_argmax_finish(slot=k & 1, rule=lm.RULE_AVX2)
         kms = pli.last_kernel_ms
-        if world > 1:  # global argmax: all-gather of per-column winners over NVLink, then merge
-            with torch.cuda.stream(xstream):
-                res = xchg.merge(res, r0, rows_global, lm.RULE_AVX2)
+        if world > 1:  # global argmax over all slabs (every rank computes the same cell)
+            res = xchg.finish(k & 1, row_offsets, rows_global, lm.RULE_AVX2)
         return res, kms
 
-    def run_steps(n):
+    def run_steps(n, sampler=None):
         out = []
         launch(0)
         for k in range(n):
             if k + 1 < n:
                 launch(k + 1)
+            if sampler is not None and world == 1 and n >= 4 and k in (n // 4, n // 2, (3 * n) // 4):
+                sampler.sample_nvml()  # the GPU is busy with scans k and k + 1 here
             out.append(finish(k))
+            if sampler is not None:
+                sampler.sample_kernel(pli.last_sm_clock_mhz)
         return out
 
     def sync_all():
@@ -235,17 +245,20 @@ def run_ours(args):
 
     run_steps(max(args.warmup, 1))
     stats = pli.last_stats
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = pli.kernel_launches
+    if sampler is not None:
+        sampler.sample_nvml()  # before the barrier: the stall an NVML query causes is over when timing starts
     sync_all()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    results = run_steps(args.steps)
+    results = run_steps(args.steps, sampler)
     e1.record(stream)
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.sample_nvml()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.result() if rank == 0 else None
     res = results[-1][0]
     kernel_ms = [r[1] for r in results]
     ms = e0.elapsed_time(e1)
@@ -309,7 +322,7 @@ def run_ours(args):
             dt = float(t.item())
         e2e = {"value": total / (dt / n_e2e) / 1e9, "unit": "Gbp/s",
                "h2d_bytes_per_step": int(harr.nbytes) * world + int(pssm.nbytes) * world,
-               "d2h_bytes_per_step": 32 * 8 * world + 4 * world,
+               "d2h_bytes_per_step": 272 * world,
                "steps": n_e2e, "api": "lm_seq_from_striped(pinned host StripedSequence) + lm_seq_score_argmax_f32"}
         if world == 1:
             assert r_e2e["position"] == res["position"], (r_e2e, res)
@@ -330,7 +343,7 @@ def run_ours(args):
                 "method": "LM_OPT_PRUNE=auto: integer upper bound for every cell (PRMT byte lanes), exact sequential "
                           "f32 sum only where the bound reaches the running maximum; result bit-identical to "
                           "scoring every cell (checked in-run against exact_everywhere)",
-                "parallelism": f"row-sharded x{world}, all-gather of per-column winners" if world > 1 else "1 GPU",
+                "parallelism": f"row-sharded x{world}, NCCL all-gather of the 272-byte winner blocks (device-resident)" if world > 1 else "1 GPU",
                 "result": {"position": res["position"], "score": res["score"]},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

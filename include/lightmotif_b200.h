@@ -105,6 +105,11 @@ uint64_t lm_ctx_kernel_launches(const lm_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) spent in the kernels
  * of the most recent scoring call */
 float lm_ctx_last_kernel_ms(const lm_ctx *ctx);
+/* SM clock (MHz) the most recent filtered fused scan actually ran at: SM cycle
+ * counter / global nanosecond timer read inside the kernel (0 when unknown).
+ * Measured on the device because NVML queries from the host stall concurrent
+ * multi-GPU work on some hosts. */
+float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
 /* Options.  LM_OPT_PRUNE controls how the FUSED calls (score+argmax,
  * score+threshold; DNA) find their result: 0 = score every cell exactly,
  * 1 (default) = exact filter + recheck when the cost model expects it to pay
@@ -266,6 +271,16 @@ int lm_seq_score_argmax_f32_launch(lm_ctx *ctx, const lm_seq *seq,
 int lm_seq_score_argmax_f32_finish(lm_ctx *ctx, int slot, int rule,
                                    lm_hit *best, lm_colwin *per_column,
                                    float *first_cell);
+/* Device address of the 272-byte result block a `launch` on `slot` writes
+ * (valid once the launch's kernels have run, in stream order): uint64
+ * key[32] -- per-column winner, (order-preserving f32 key << 32) | row relative
+ * to row_begin, 0 = no valid cell -- then uint32 first_cell (f32 bits of cell
+ * (row_begin, 0)) and 12 bytes of padding.  Lets a multi-GPU host hand the
+ * winners to NCCL (all-gather) without a round trip through host memory;
+ * decode with lm_decode_keys, merge with lm_argmax_merge. */
+void *lm_ctx_result_block(lm_ctx *ctx, int slot);
+/* keys[32] (as stored in a result block) -> lm_colwin[32] */
+void lm_decode_keys(const uint64_t *keys, lm_colwin *out);
 /* FUSED score + Threshold::threshold (scores.rs:207-213): all cells >= t of
  * the scored rows, row-major order, exact f32 scores. */
 int lm_seq_score_threshold_f32(lm_ctx *ctx, const lm_seq *seq,

@@ -269,11 +269,20 @@ class Pipeline:
         return capi.lib().lm_ctx_last_kernel_ms(self._ctx)
 
     @property
+    def last_sm_clock_mhz(self):
+        """SM clock the last filtered scan ran at, measured inside the kernel (lm_ctx_last_sm_clock_mhz)."""
+        return float(capi.lib().lm_ctx_last_sm_clock_mhz(self._ctx))
+
+    @property
     def stream(self):
         return capi.lib().lm_ctx_stream(self._ctx)
 
     def synchronize(self):
         self._check(capi.lib().lm_ctx_synchronize(self._ctx))
+
+    def result_block_ptr(self, slot=0):
+        """Device address of the 272-byte result block of launch slot `slot` (lm_ctx_result_block)."""
+        return int(capi.lib().lm_ctx_result_block(self._ctx, int(slot)))
 
     def set_prune(self, mode):
         """LM_OPT_PRUNE: 0 = score every cell, 1 = auto (default), 2 = filter whenever possible."""
@@ -429,6 +438,23 @@ class Pipeline:
 
 
 COLWIN_DTYPE = np.dtype([("row", np.uint64), ("score", np.float32), ("valid", np.uint32)])  # == lm_colwin
+
+
+def f32_key(x):
+    """Order-preserving u32 key of f32 values (common.cuh f32_to_key), vectorised."""
+    b = np.asarray(x, dtype=np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+RESULT_BLOCK_WORDS = 34  # uint64 words of a result block: 32 column keys, first_cell, padding
+
+
+def decode_keys(keys):
+    """uint64[32] column keys of a result block -> numpy array of COLWIN_DTYPE (lm_decode_keys)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(LANES, dtype=COLWIN_DTYPE)
+    capi.lib().lm_decode_keys(_ptr(keys), out.ctypes.data_as(C.POINTER(ColWin)))
+    return out
 
 
 def argmax_merge(parts, row_offsets, first_cell, total_rows, rule=RULE_AVX2):

@@ -43,14 +43,14 @@ _lib = None
 SYMBOLS = [
     "lm_abi_version", "lm_strerror", "lm_ctx_last_error", "lm_ctx_create", "lm_ctx_create_on_stream",
     "lm_ctx_destroy", "lm_ctx_stream", "lm_ctx_synchronize", "lm_ctx_kernel_launches",
-    "lm_ctx_last_kernel_ms", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
+    "lm_ctx_last_kernel_ms", "lm_ctx_last_sm_clock_mhz", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
     "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_argmax_u8", "lm_max_u8",
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
     "lm_seq_from_striped", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
-    "lm_seq_score_argmax_f32_batch", "lm_argmax_merge",
+    "lm_seq_score_argmax_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
 ]
 
 
@@ -87,6 +87,8 @@ def _declare(L):
     L.lm_ctx_kernel_launches.restype = C.c_uint64
     L.lm_ctx_last_kernel_ms.argtypes = [vp]
     L.lm_ctx_last_kernel_ms.restype = C.c_float
+    L.lm_ctx_last_sm_clock_mhz.argtypes = [vp]
+    L.lm_ctx_last_sm_clock_mhz.restype = C.c_float
     L.lm_ctx_set_option.argtypes = [vp, i, i]
     L.lm_ctx_last_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     L.lm_encode.argtypes = [vp, i, vp, sz, vp, szp]
@@ -121,6 +123,10 @@ def _declare(L):
     L.lm_seq_score_threshold_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, C.c_float, hitp, sz, szp]
     L.lm_seq_score_argmax_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, hitp]
     L.lm_argmax_merge.argtypes = [cwp, sz, vp, C.c_float, C.c_uint64, i, hitp]
+    L.lm_ctx_result_block.argtypes = [vp, i]
+    L.lm_ctx_result_block.restype = vp
+    L.lm_decode_keys.argtypes = [vp, cwp]
+    L.lm_decode_keys.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("lm_abi_version",):

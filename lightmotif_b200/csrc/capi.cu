@@ -41,6 +41,7 @@ struct lm_ctx {
   int opt_reserve_sms = 0;                // LM_OPT_RESERVE_SMS: SMs left free for concurrent (NCCL) kernels
   size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
   uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
+  float sm_mhz = 0.f;                     // SM clock the last filtered scan ran at (cycle counter / global timer)
   // the last matrix uploaded to d_table / d_table2 and the last filter plan: a
   // caller scanning many sequences (or benchmarking) with one PSSM pays for the
   // host-side set-up once
@@ -350,7 +351,7 @@ int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
 struct SmallBlock {
   ColKeys ck;                    // 260 bytes (+4 pad)
   unsigned long long count;      // @264
-  unsigned long long stats[3];   // @272
+  unsigned long long stats[5];   // @272: candidates, overflow tiles, tile counter, SM cycles, ns (CTA 0's producer)
 };
 static_assert(offsetof(SmallBlock, count) == 264 && offsetof(SmallBlock, stats) == 272, "small block layout");
 
@@ -508,6 +509,8 @@ int lm_ctx_last_stats(const lm_ctx* ctx, uint64_t out[4]) {
   for (int i = 0; i < 4; ++i) out[i] = ctx->stats[i];
   return LM_OK;
 }
+
+float lm_ctx_last_sm_clock_mhz(const lm_ctx* ctx) { return ctx ? ctx->sm_mhz : 0.f; }
 
 float lm_ctx_last_kernel_ms(const lm_ctx* ctx) {
   if (!ctx) return 0.f;
@@ -1037,12 +1040,22 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
   ctx->stats[1] = sl.pruned ? sb->stats[1] : 0;
   ctx->stats[2] = sl.pruned ? 1 : 0;
   ctx->stats[3] = sl.pruned ? (uint64_t)sl.r : 0;
+  ctx->sm_mhz = (sl.pruned && sb->stats[4]) ? (float)((double)sb->stats[3] * 1e3 / (double)sb->stats[4]) : 0.f;
   lm_colwin cw[32];
   decode_colwins(sb->ck.keys, false, cw);
   if (per_column) std::memcpy(per_column, cw, sizeof(cw));
   const float fc = bits_to_score(sb->ck.first_cell, false);
   if (first_cell) *first_cell = fc;
   return apply_rule(cw, fc, rule, false, sl.n_rows, 0, best);
+}
+
+void* lm_ctx_result_block(lm_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 1 || !ctx->d_small.p) return nullptr;
+  return (uint8_t*)ctx->d_small.p + (size_t)slot * 1024;
+}
+
+void lm_decode_keys(const uint64_t* keys, lm_colwin* out) {
+  if (keys && out) decode_colwins((const unsigned long long*)keys, false, out);
 }
 
 int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,

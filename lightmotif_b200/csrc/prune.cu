@@ -180,6 +180,13 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     // counter, so the CTAs of the whole grid sweep the sequence as one dense window.
     uint32_t thr_key = 0xffffffffu, bias4 = 0;
     float thr = THR ? a.thr : -INFINITY;
+    // CTA 0 measures the SM clock the scan runs at: cycle counter vs global nanosecond timer
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
+    if (blockIdx.x == 0 && lane == 0) {
+      clk0 = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
     for (uint32_t it = 0;; ++it) {
       const int s = it % NSTAGE;
       // claim the tile and fetch the running maximum first: both round trips overlap the wait
@@ -230,6 +237,12 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         }
       }
       if (tile >= num_tiles) break;
+    }
+    if (blockIdx.x == 0 && lane == 0 && a.stats) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      a.stats[3] = (unsigned long long)(clock64() - clk0);
+      a.stats[4] = ns1 - ns0;
     }
     return;
   }

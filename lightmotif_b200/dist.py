@@ -2,8 +2,8 @@
 
 The path shards by striped rows with no data-path collective:
 rank g owns rows [r_g, r_{g+1}) of the GLOBAL striped matrix (+ M-1 halo
-rows).  The only exchange is one all-gather of 33 small records per rank
-(32 per-column winners + the first cell), merged on every rank with
+rows).  The only exchange is one all-gather of the 272-byte result block per rank
+(32 packed per-column winners + the first cell), merged on every rank with
 ``lm_argmax_merge`` so the result is the cell a single call over the whole
 matrix would return (later slabs win row ties, then the back-end's rule).
 """
@@ -21,47 +21,80 @@ def shard_rows(rows_global: int, world: int, rank: int):
     return rows_global * rank // world, rows_global * (rank + 1) // world
 
 
-def pack_winners(columns, first_cell, row_begin):
-    """[33, 3] float64 (numpy): rows 0..31 = (row, score, valid), row 32 =
-    (row_begin, first_cell, 1).  float64 holds 32-bit rows and f32 scores exactly."""
-    t = np.zeros((LANES + 1, 3), dtype=np.float64)
-    if isinstance(columns, np.ndarray):
-        t[:LANES, 0], t[:LANES, 1], t[:LANES, 2] = columns["row"], columns["score"], columns["valid"]
-    else:
-        t[:LANES] = np.asarray(columns, dtype=np.float64)
-    t[LANES] = (float(row_begin), float(first_cell), 1.0)
-    return t
+class _DeviceWords:
+    """__cuda_array_interface__ view of `n` uint64 words at a raw device address."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
 
 
 class WinnerExchange:
-    """Preallocated buffers for the per-step all-gather of the winners
-    (33 x 3 doubles per rank; latency-bound, so no per-step allocations)."""
+    """The per-scan exchange of a row-sharded argmax, device-resident: the 272-byte result block
+    the scan kernels leave in HBM (32 packed per-column winners + the first cell) is all-gathered
+    straight from there over NCCL/NVLink on the scan's own stream -- no round trip through host
+    memory, no host synchronisation -- and only the gathered blocks (world x 272 bytes) are copied
+    to pinned host memory, where `finish` applies the tie rule with ``lm_argmax_merge``.  Two slots,
+    so the exchange of scan k overlaps scan k + 1.
+
+    With the gloo backend (CPU tests) the blocks are host arrays passed to `enqueue` directly."""
 
     def __init__(self, device=None, group=None):
+        from . import RESULT_BLOCK_WORDS
         self.group, self.device = group, device
         self.world = dist.get_world_size(group)
-        self.mine = torch.empty((LANES + 1, 3), dtype=torch.float64, device=device)
-        self.all = torch.empty((self.world * (LANES + 1), 3), dtype=torch.float64, device=device)
-        pin = device is not None and torch.device(device).type == "cuda"
-        self.host_in = torch.empty((LANES + 1, 3), dtype=torch.float64, pin_memory=pin)
-        self.host_out = torch.empty((self.world * (LANES + 1), 3), dtype=torch.float64, pin_memory=pin)
+        self.words = RESULT_BLOCK_WORDS
+        self.cuda = device is not None and torch.device(device).type == "cuda"
+        self.all = [torch.empty((self.world, self.words), dtype=torch.int64, device=device) for _ in range(2)]
+        self.host = [torch.empty((self.world, self.words), dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
+        self.events = [torch.cuda.Event() for _ in range(2)] if self.cuda else [None, None]
+        self._views = {}
+
+    def enqueue(self, block, slot=0):
+        """`block`: device address (int) of this rank's result block, or (CPU) an int64[34] tensor.
+        Enqueues all-gather + D2H on the current stream; returns immediately."""
+        if isinstance(block, int):
+            if block not in self._views:
+                self._views[block] = torch.as_tensor(_DeviceWords(block, self.words), device=self.device)
+            block = self._views[block]
+        dist.all_gather_into_tensor(self.all[slot], block.reshape(1, self.words), group=self.group)
+        self.host[slot].copy_(self.all[slot], non_blocking=True)
+        if self.cuda:
+            self.events[slot].record()
+
+    def finish(self, slot, row_offsets, rows_global, rule=RULE_AVX2):
+        """Wait for `slot`'s exchange and merge: the cell one call over the whole matrix returns."""
+        from . import decode_keys
+        if self.cuda:
+            self.events[slot].synchronize()
+        blocks = self.host[slot].numpy().view(np.uint64)
+        parts = np.stack([decode_keys(blocks[r, :LANES]) for r in range(self.world)])
+        first_cell = float(np.array([blocks[0, LANES] & np.uint64(0xFFFFFFFF)], dtype=np.uint64).astype(np.uint32).view(np.float32)[0])
+        offsets = np.asarray(list(row_offsets) + [rows_global], dtype=np.uint64)
+        return argmax_merge(parts, offsets, first_cell, rows_global, rule)
 
     def merge(self, local, row_begin, rows_global, rule=RULE_AVX2):
-        if local is None:
-            packed = pack_winners(np.zeros((LANES, 3)), 0.0, row_begin)
-        else:
-            packed = pack_winners(local["columns"], local["first_cell"], row_begin)
-        self.host_in.numpy()[:] = packed
-        self.mine.copy_(self.host_in, non_blocking=True)
-        dist.all_gather_into_tensor(self.all, self.mine, group=self.group)
-        self.host_out.copy_(self.all, non_blocking=False)
-        out = self.host_out.numpy().reshape(self.world, LANES + 1, 3)
-        parts = np.zeros((self.world, LANES), dtype=COLWIN_DTYPE)
-        parts["row"] = out[:, :LANES, 0].astype(np.uint64)
-        parts["score"] = out[:, :LANES, 1].astype(np.float32)
-        parts["valid"] = out[:, :LANES, 2].astype(np.uint32)
-        offsets = np.concatenate([out[:, LANES, 0], [rows_global]]).astype(np.uint64)
-        return argmax_merge(parts, offsets, float(out[0, LANES, 1]), rows_global, rule)
+        """Host-input convenience form (one synchronous exchange): `local` = result of
+        DeviceSequence.score_argmax(..., with_columns="numpy") on this rank's slab, or None."""
+        from . import f32_key
+        blk = np.zeros(self.words, dtype=np.uint64)
+        if local is not None:
+            cols = local["columns"]
+            if not isinstance(cols, np.ndarray):
+                arr = np.zeros(LANES, dtype=COLWIN_DTYPE)
+                for i, (r, sc, v) in enumerate(cols):
+                    arr[i] = (r, sc, v)
+                cols = arr
+            keys = (f32_key(cols["score"]).astype(np.uint64) << np.uint64(32)) | cols["row"].astype(np.uint64)
+            blk[:LANES] = np.where(cols["valid"] != 0, keys, np.uint64(0))
+            blk[LANES] = np.array([local["first_cell"]], dtype=np.float32).view(np.uint32)[0]
+        t = torch.from_numpy(blk.view(np.int64).copy())
+        if self.cuda:
+            t = t.to(self.device)
+        starts = torch.tensor([row_begin], dtype=torch.int64, device=self.device if self.cuda else None)
+        all_starts = torch.empty(self.world, dtype=torch.int64, device=starts.device)
+        dist.all_gather_into_tensor(all_starts, starts, group=self.group)
+        self.enqueue(t, 0)
+        return self.finish(0, [int(x) for x in all_starts.cpu().tolist()], rows_global, rule)
 
 
 def allgather_merge(local, row_begin, rows_global, rule=RULE_AVX2, device=None, group=None):
