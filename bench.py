@@ -207,6 +207,8 @@ def run_ours(args):
 
     xchg = lmdist.WinnerExchange(device=dev) if world > 1 else None
     row_offsets = [rows_global * r // world for r in range(world)]
+    if world > 1 and args.reserve_sms:
+        pli.set_reserve_sms(args.reserve_sms)  # room for the NCCL kernel of scan k beside scan k + 1
 
     # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners: an NCCL
     # all-gather of the 272-byte result block straight from HBM, enqueued on the scan's stream, and
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs the scan grid leaves free for the NCCL kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -15,6 +15,7 @@
 //   Pipeline::threshold                   trait Threshold<T, C>      pli/mod.rs:204-222
 //   EncodedSequence / StripedSequence     seq.rs:100-175, 288-381
 //   StripedScores                         scores.rs:101-213
+//   Scanner                               scan.rs:96-250
 //   CountMatrix -> FrequencyMatrix -> WeightMatrix -> ScoringMatrix -> DiscreteMatrix
 //                                         pwm/mod.rs:150-258, 376-430, 513-526, 640-696, 763-790
 //
@@ -636,6 +637,42 @@ class Pipeline {
 
   std::shared_ptr<lm_ctx> ctx_;
   int rule_ = LM_RULE_AVX2;
+};
+
+// ------------------------------------------------------------------ Scanner
+// Mirror of lightmotif::scan::Scanner (scan.rs:96-250) on a resident sequence.  The reference scans
+// blocks of rows with the u8 DiscreteMatrix, thresholds the u8 scores and rescores the survivors in
+// f32; here the same filter + exact recheck runs inside one fused kernel over the whole sequence, so
+// block_size() is accepted and ignored.  Hits: positions p with p + M <= len whose exact f32 score
+// is >= threshold (scan.rs:186-191).  max(): best hit, ties towards the larger position (scan.rs:235).
+template <typename A>
+class Scanner {
+ public:
+  Scanner(const Pipeline<A>& pli, const ScoringMatrix<A>& pssm, const DeviceSequence<A>& seq)
+      : pli_(pli), pssm_(pssm), seq_(seq) {}
+  Scanner& threshold(float t) { threshold_ = t; return *this; }
+  Scanner& block_size(size_t b) { block_size_ = b; return *this; }
+  std::vector<Hit> collect() const {
+    std::vector<Hit> hits = pli_.score_threshold(pssm_, seq_, threshold_);
+    hits.erase(std::remove_if(hits.begin(), hits.end(),
+                              [&](const Hit& h) { return h.position + pssm_.len() > seq_.len(); }), hits.end());
+    std::sort(hits.begin(), hits.end(), [](const Hit& a, const Hit& b) { return a.position < b.position; });
+    return hits;
+  }
+  std::optional<Hit> max() const {
+    Pipeline<A> p = pli_;
+    p.set_argmax_rule(LM_RULE_SSE2);  // last column, last row among equal maxima = largest position
+    auto best = p.score_argmax(pssm_, seq_);
+    if (!best || !(best->score >= threshold_)) return std::nullopt;
+    return best;
+  }
+
+ private:
+  Pipeline<A> pli_;
+  const ScoringMatrix<A>& pssm_;
+  const DeviceSequence<A>& seq_;
+  float threshold_ = 0.0f;
+  size_t block_size_ = 256;
 };
 
 template <typename A>

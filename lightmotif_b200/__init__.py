@@ -223,6 +223,47 @@ class DeviceSequence:
         return [_hit(b) for b in best]
 
 
+class Scanner:
+    """Mirror of ``lightmotif::scan::Scanner`` (scan.rs:96-250) on a resident sequence.
+
+    The reference scans blocks of rows with the u8 DiscreteMatrix, thresholds the u8 scores and
+    rescores the survivors exactly in f32; here the same filter + exact recheck runs inside ONE fused
+    kernel over the whole sequence (prune.cu), so `block_size` is accepted and ignored.  Hits are the
+    positions p with p + M <= len(seq) whose exact f32 score is >= threshold (scan.rs:186-191), each
+    with that exact score.  `max()` returns the best hit, ties resolved towards the larger position
+    (scan.rs:235); it searches every position exactly, i.e. it does not reproduce the reference's
+    dependence on the u8 rounding of near-ties."""
+
+    def __init__(self, pssm, seq):
+        self.pssm, self.seq, self._threshold, self._block_size = np.asarray(pssm, dtype=np.float32), seq, 0.0, 256
+
+    def threshold(self, t):
+        self._threshold = float(t)
+        return self
+
+    def block_size(self, b):
+        self._block_size = int(b)
+        return self
+
+    def collect(self):
+        m = len(self.pssm)
+        hits = self.seq.score_threshold(self.pssm, self._threshold)
+        out = [{"position": h["position"], "score": h["score"]} for h in hits if h["position"] + m <= self.seq.length]
+        out.sort(key=lambda h: h["position"])
+        return out
+
+    def __iter__(self):
+        return iter(self.collect())
+
+    def max(self):
+        # the SSE2 rule keeps the LAST column among equal maxima and the last row within it, i.e.
+        # the largest position col * rows + row -- the Scanner's tie-break
+        best = self.seq.score_argmax(self.pssm, rule=RULE_SSE2)
+        if best is None or not (best["score"] >= self._threshold):
+            return None
+        return {"position": best["position"], "score": best["score"]}
+
+
 class Pipeline:
     """``Pipeline::<A, Cuda>::cuda()``: the CUDA back-end of the pipeline traits
     (Encode / Stripe / Score / Maximum / Threshold, pli/mod.rs:34-222)."""

@@ -47,6 +47,7 @@ class WinnerExchange:
         self.all = [torch.empty((self.world, self.words), dtype=torch.int64, device=device) for _ in range(2)]
         self.host = [torch.empty((self.world, self.words), dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
         self.events = [torch.cuda.Event() for _ in range(2)] if self.cuda else [None, None]
+        self.side = torch.cuda.Stream(device=device) if self.cuda else None
         self._views = {}
 
     def enqueue(self, block, slot=0):
@@ -56,9 +57,17 @@ class WinnerExchange:
             if block not in self._views:
                 self._views[block] = torch.as_tensor(_DeviceWords(block, self.words), device=self.device)
             block = self._views[block]
-        dist.all_gather_into_tensor(self.all[slot], block.reshape(1, self.words), group=self.group)
-        self.host[slot].copy_(self.all[slot], non_blocking=True)
-        if self.cuda:
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.all[slot], block.reshape(1, self.words), group=self.group)
+            self.host[slot].copy_(self.all[slot])
+            return
+        # the collective is ordered after the scan that produced `block` (NCCL's stream waits for the
+        # current stream), but the current stream does NOT wait for it: the next scan starts at once
+        # and the gather + copy-out complete beside it on a side stream
+        work = dist.all_gather_into_tensor(self.all[slot], block.reshape(1, self.words), group=self.group, async_op=True)
+        with torch.cuda.stream(self.side):
+            work.wait()
+            self.host[slot].copy_(self.all[slot], non_blocking=True)
             self.events[slot].record()
 
     def finish(self, slot, row_offsets, rows_global, rule=RULE_AVX2):

@@ -153,6 +153,13 @@ static void test_resident(const Pipeline<Dna>& pli) {  // fused calls on a resid
   for (auto& h : hits) pos.push_back(h.position);
   std::sort(pos.begin(), pos.end());
   CHECK(pos == (std::vector<size_t>{18, 27, 32}));  // scan.rs:279-315
+  // scan.rs:279-333: Scanner hits 18 / 27 / 32 at threshold -10, max -5.50167 @ 18
+  Scanner<Dna> scanner(pli, pssm, dev);
+  auto sh = scanner.threshold(-10.0f).block_size(16).collect();
+  CHECK(sh.size() == 3 && sh[0].position == 18 && sh[1].position == 27 && sh[2].position == 32);
+  auto smax = scanner.max();
+  CHECK(smax.has_value() && smax->position == 18 && std::fabs(smax->score + 5.50167f) < 1e-5f);
+  CHECK(!Scanner<Dna>(pli, pssm, dev).threshold(0.0f).max().has_value());
   bool thrown = false;
   try {
     pli.upload_ascii("ATG.", 3);

@@ -230,6 +230,41 @@ def test_score_ecoli(dna, kat, ecoli_codes, ecoli_kat):
     assert [(h["row"], h["col"]) for h in hits] == list(zip(ro.tolist(), co.tolist()))
 
 
+@pytest.mark.parametrize("pc", [0.1, 0.0])
+def test_scanner_consistency(lm, dna, kat, ecoli_codes, pc):
+    """tests/scan.rs:9-83 on the device: Scanner hits over the full E. coli genome (3 patterns,
+    threshold 5.0, pseudocount 0.1 and 0.0 = -inf cells) == the oracle's Scanner == brute force,
+    exact f32 scores; scan.rs:235 tie rule for max()."""
+    s = kat["scan"]
+    pssm = O.pssm_from_sequences(O.DNA, s["patterns"], pc)
+    n = ecoli_codes.size
+    st = O.stripe(O.DNA, ecoli_codes, 32, s["wrap"])
+    wpos, wsc = O.scanner_collect(O.DNA, pssm, st, s["wrap"], n, s["threshold"], 256)
+    order = np.argsort(wpos)
+    seq = dna.sequence_from_symbols(ecoli_codes, s["wrap"])
+    for prune in (1, 0):
+        dna.set_prune(prune)
+        hits = lm.Scanner(pssm, seq).threshold(s["threshold"]).block_size(64).collect()
+        assert [h["position"] for h in hits] == wpos[order].tolist()
+        assert np.array_equal(bits(np.array([h["score"] for h in hits], np.float32)), bits(wsc[order]))
+    dna.set_prune(1)
+    best = lm.Scanner(pssm, seq).threshold(s["threshold"]).max()
+    full = O.score_f32(pssm, st, n, wrap=s["wrap"])
+    flat = O.unstripe(full, n - len(pssm) + 1)
+    top = flat.max()
+    assert best["score"] == float(top) and best["position"] == int(np.flatnonzero(flat == top)[-1])
+    assert lm.Scanner(pssm, seq).threshold(float(top) + 1.0).max() is None
+
+
+def test_scanner_max_ecoli_tenth(lm, dna, kat, ecoli_codes):
+    """tests/argmax.rs:76-107: Scanner::max on the first tenth of E. coli == last maximum (401649)."""
+    k = kat["ecoli_tenth"]
+    pssm = O.pssm_from_sequences(O.DNA, k["patterns"], 0.1)
+    seq = dna.sequence_from_symbols(ecoli_codes[: k["n"]], 14)
+    best = lm.Scanner(pssm, seq).max()
+    assert best["position"] == k["argmax_pipeline"]
+
+
 def test_score_u8(dna, kat, ecoli_codes):
     d = kat["dna"]
     pssm = O.pssm_from_sequences(O.DNA, d["patterns"], d["pseudocount"])
