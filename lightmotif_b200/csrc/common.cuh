@@ -66,20 +66,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// same, with an explicit suspend-time hint (ns): a waiting warp sleeps in hardware instead of
-// burning issue slots in the retry loop; it is woken as soon as the phase completes
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+// wait with back-off: between polls the warp really sleeps (nanosleep), so a waiting warp costs a
+// handful of issue slots per microsecond instead of spinning through the retry loop (the hinted form
+// of try_wait compiles to a TRYWAIT + NANOSLEEP.SYNCS loop that wakes on every barrier event of the
+// CTA: profiles/README.md, r01 v5)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(ns)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,

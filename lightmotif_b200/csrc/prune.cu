@@ -2,7 +2,7 @@
 //
 // Kernel.  One CTA = 8 consumer (filter) warps + 1 producer warp, persistent.
 //
-//  producer claims tiles (8 x 4 x PL = 864 striped rows x 32 columns = 27 648 positions) one at a
+//  producer claims tiles (8 x 4 x PL = 992 striped rows x 32 columns = 31 744 positions) one at a
 //           time from a global counter -- so the whole grid sweeps the sequence as one dense
 //           window --, stages each tile (+ halo) from HBM with ONE bulk-TMA copy into a ring of
 //           NSTAGE shared-memory buffers (full[s] / empty[s] mbarriers), and publishes with each
@@ -43,6 +43,15 @@ namespace {
 
 constexpr int PW = 8;                   // consumer (filter) warps per CTA
 constexpr int PT = (PW + 1) * 32;       // + one producer warp
+#ifndef LM_PRUNE_G
+#define LM_PRUNE_G LM_PRUNE_PL  // rows per look-up block (operand reuse, accumulator ILP, one test per block)
+#endif
+#ifndef LM_PRUNE_PSLEEP
+#define LM_PRUNE_PSLEEP 200  // ns between the producer's polls of an `empty` barrier
+#endif
+#ifndef LM_PRUNE_CSLEEP
+#define LM_PRUNE_CSLEEP 100  // ns between a consumer warp's polls of a `full` barrier
+#endif
 #ifndef LM_PRUNE_EXP
 #define LM_PRUNE_EXP 0
 #endif
@@ -51,7 +60,7 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #endif
 constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 #ifndef LM_PRUNE_PL
-#define LM_PRUNE_PL 27
+#define LM_PRUNE_PL 31
 #endif
 #ifndef LM_PRUNE_MINBLOCKS
 #define LM_PRUNE_MINBLOCKS 3
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
       }
-      if (it >= NSTAGE) mbar_wait_hint(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, 4000);
+      if (it >= NSTAGE) mbar_wait_backoff(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
       // ---- current threshold -> byte bias (recomputed only when the threshold moved)
       if (THR ? it == 0 : sk != thr_key) {
         const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
 
   for (uint32_t it = 0;; ++it) {
     const int s = it % NSTAGE;
-    mbar_wait_hint(&ctl->full[s], (it / NSTAGE) & 1, 2000);
+    mbar_wait_backoff(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
     const uint64_t tile = ctl->desc[s].tile;
     if (tile >= num_tiles) break;
     const uint32_t bias4 = ctl->desc[s].bias4;
@@ -346,22 +355,56 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           nq += __popc(votes);
         }
       };
-      uint32_t prev = 0;
+      // Rows are processed in blocks of G (default: the thread's whole run of PL rows): the look-up
+      // loop runs k-outer / row-inner, so that consecutive PRMTs share their two table registers
+      // (operand reuse: PRMT is limited by register-file ports, not only by the ALU pipe -- measured
+      // +13 % from G = 2 to G = PL) and independent accumulator chains hide the IMAD latency.  One
+      // test covers the whole block (OR of the accumulators & mask); the rare hit re-tests pair by
+      // pair.
+      constexpr int G = LM_PRUNE_G;
 #pragma unroll
-      for (int i = 0; i < PL; ++i) {
-        if (PAIR) {
-          const uint32_t nx = make_sel(rp[(i + W - 1) * 8]);
-          sel[i + W - 2] = combine(raw_prev, nx);
-          raw_prev = nx;
-        } else {
-          sel[i + W - 1] = make_sel(rp[(i + W - 1) * 8]);
+      for (int i0 = 0; i0 < PL; i0 += G) {
+        const int g = (PL - i0) < G ? (PL - i0) : G;  // compile-time after unrolling
+#pragma unroll
+        for (int ii = 0; ii < G; ++ii) {
+          if (ii < g) {
+            const int i = i0 + ii;
+            if (PAIR) {
+              const uint32_t nx = make_sel(rp[(i + W - 1) * 8]);
+              sel[i + W - 2] = combine(raw_prev, nx);
+              raw_prev = nx;
+            } else {
+              sel[i + W - 1] = make_sel(rp[(i + W - 1) * 8]);
+            }
+          }
         }
-        uint32_t acc = bias4;
+        uint32_t acc[G];
 #pragma unroll
-        for (int k = 0; k < R; ++k) acc = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc);
-        if (i & 1) push2(prev, acc, i - 1);          // one test per PAIR of quad rows
-        else if (i == PL - 1) push2(acc, 0u, i);
-        prev = acc;
+        for (int ii = 0; ii < G; ++ii) acc[ii] = bias4;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+#pragma unroll
+          for (int ii = 0; ii < G; ++ii) {
+            if (ii < g) {
+#if LM_PRUNE_EXP == 3  // experiment: one table register per look-up (valid only when tab_hi == 0)
+              acc[ii] = add_fma_pipe(prmt_raw(tlo[k], 0u, sel[i0 + ii + STEP * k]), one, acc[ii]);
+#else
+              acc[ii] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i0 + ii + STEP * k]), one, acc[ii]);
+#endif
+            }
+          }
+        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int ii = 0; ii < G; ++ii)
+          if (ii < g) any |= acc[ii];
+        if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0)) {
+#pragma unroll
+          for (int ii = 0; ii < G; ii += 2) {
+            if (ii + 1 < g) push2(acc[ii], acc[ii + 1], i0 + ii);
+            else if (ii < g) push2(acc[ii], 0u, i0 + ii);
+          }
+        }
       }
       __syncwarp();  // queue complete
 
