@@ -42,6 +42,18 @@ def rest_pssm():
     return O.pssm_from_counts(O.DNA, z["rest"], 0.1)
 
 
+def measured_traffic(per_gpu_bp, pruned):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json); only when the capture is of this workload."""
+    p = REPO / "profiles" / "ncu_traffic.json"
+    if not (p.exists() and pruned):
+        return None
+    d = json.loads(p.read_text())
+    if int(d.get("launch_bp", 0)) != int(per_gpu_bp):
+        return None
+    return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+
+
 def measured_peaks():
     p = REPO / "MEASURED_PEAKS.json"
     if p.exists():
@@ -342,15 +354,17 @@ def run_ours(args):
                             f"per GPU, fused score+argmax (configs[1]; x{world} GPUs row-sharded)",
                 "bp_per_gpu": per_gpu, "total_bp": total, "seed": SEED,
                 "l2": "input per GPU (5 GB) exceeds L2 (126 MB); no flush needed",
-                "method": "LM_OPT_PRUNE=auto: integer upper bound for every cell (PRMT byte lanes), exact sequential "
-                          "f32 sum only where the bound reaches the running maximum; result bit-identical to "
-                          "scoring every cell (checked in-run against exact_everywhere)",
+                "method": "LM_OPT_PRUNE=auto: integer upper bound for every cell (PRMT byte-lane look-ups, 4 cells per "
+                          "instruction), exact sequential f32 sum only where the bound reaches the running maximum; "
+                          "result bit-identical to scoring every cell (checked in-run against exact_everywhere)",
                 "parallelism": f"row-sharded x{world}, NCCL all-gather of the 272-byte winner blocks (device-resident)" if world > 1 else "1 GPU",
                 "result": {"position": res["position"], "score": res["score"]},
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": how,
-                         "kernel": (f"lm::prune_kernel<{stats['filter_rows']}, argmax> (exact filter + recheck; "
+                         "frac": achieved / peak, "traffic": measured_traffic(per_gpu, stats["pruned"]),
+                         "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "launch, ncu --set full)", "peak_source": how,
+                         "kernel": (f"lm::prune_kernel<{stats['filter_rows']}, {'paired' if stats.get('paired') else 'single'}, argmax> (exact filter + recheck; "
                                     "+ lm::score_kernel on the first 262144 rows)") if stats["pruned"]
                          else "lm::score_kernel<16, MODE_ARGMAX, f32>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": positions,

@@ -47,10 +47,10 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #define LM_PRUNE_G LM_PRUNE_PL  // rows per look-up block (operand reuse, accumulator ILP, one test per block)
 #endif
 #ifndef LM_PRUNE_PSLEEP
-#define LM_PRUNE_PSLEEP 200  // ns between the producer's polls of an `empty` barrier
+#define LM_PRUNE_PSLEEP 50   // ns between the producer's polls of an `empty` barrier
 #endif
 #ifndef LM_PRUNE_CSLEEP
-#define LM_PRUNE_CSLEEP 100  // ns between a consumer warp's polls of a `full` barrier
+#define LM_PRUNE_CSLEEP 20   // ns between a consumer warp's polls of a `full` barrier
 #endif
 #ifndef LM_PRUNE_EXP
 #define LM_PRUNE_EXP 0
@@ -563,16 +563,20 @@ struct Unit {
 // Calibrated on B200 (profiles/README.md).
 double filter_cost(int r, int w, bool pair, double pass) {
   const double halo = (double)(PL + w - 1) / PL;
-  const double core = 2.0 * r + (pair ? 4.0 : 2.0) * halo + 2.5;
-  // slow path of the pair test: taken when any of the 64 quads of a warp pair has a candidate
+  const double core = 2.0 * r + (pair ? 5.0 : 2.0) * halo + 0.5;
+  // slow path of the per-thread-tile test: taken when any of the 32 * PL quads of a warp tile has a
+  // candidate; it re-tests the PL / 2 row pairs (~5 slots each) and appends the hits (~15 slots each)
   const double p_quad = std::min(1.0, 4.0 * pass);
-  const double push = 12.5 * (1.0 - std::pow(1.0 - p_quad, 64.0));
+  const double p_slow = 1.0 - std::pow(1.0 - p_quad, 32.0 * PL);
+  const double push = (p_slow * 2.5 * PL + 15.0 * 32.0 * PL * p_quad) / PL;
   // exact recheck, per warp tile (WARP_ROWS * 32 positions): one pass of ~130 slots per 32 flags
   const double lambda = pass * WARP_ROWS * 32.0;
   const double recheck = (130.0 * (1.0 - std::exp(-lambda)) + 130.0 * lambda * 8.0 / 32.0) / PL;
   // queue overflow => the warp rescans its slice exactly (~350 slots per quad row)
   const double overflow = lambda > QCAP / 4.0 ? 350.0 : 0.0;
-  return core + push + recheck + overflow;
+  // weights fitted to the measured sweep of forced configurations (profiles/README.md, r01 v5):
+  // the candidate paths are partly hidden behind the other warps' filter work
+  return core + 0.4 * push + 0.6 * recheck + overflow;
 }
 constexpr double EXACT_COST = 350.0;  // exact-everywhere kernel, same unit
 
