@@ -566,9 +566,10 @@ int lm_stripe(lm_ctx* ctx, int alphabet, const uint8_t* sym, size_t n, uint8_t* 
   if (!valid_alphabet(alphabet) || (n && (!sym || !dst)) || dst_stride < 32) return LM_ERR_INVALID_ARG;
   if (n == 0) return LM_OK;
   const size_t rows = (n + 31) / 32;
-  LM_CHECK(ensure(ctx, ctx->d_in, n));
+  LM_CHECK(ensure(ctx, ctx->d_in, n + 16));  // the stripe kernel reads whole 4-byte words
   LM_CHECK(ensure(ctx, ctx->d_out, rows * 32));
   LM_TRY(cudaMemcpyAsync(ctx->d_in.p, sym, n, cudaMemcpyHostToDevice, ctx->stream));
+  LM_TRY(cudaMemsetAsync((uint8_t*)ctx->d_in.p + n, 0, 16, ctx->stream));  // bytes of the last word past n
   timer_begin(ctx);
   LM_TRY(launch_stripe((const uint8_t*)ctx->d_in.p, false, n, rows, 0, rows, (uint8_t*)ctx->d_out.p,
                        alphabet, nullptr, ctx->sm_count, ctx->stream));
@@ -763,10 +764,11 @@ static int seq_from_flat(lm_ctx* ctx, int alphabet, const uint8_t* src, size_t n
   LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, n, &s));
   int st = LM_OK;
   do {
-    if ((st = ensure(ctx, ctx->d_in, std::max<size_t>(n, 1))) < 0) break;
+    if ((st = ensure(ctx, ctx->d_in, n + 16)) < 0) break;  // the stripe kernel reads whole 4-byte words
     unsigned long long* d_bad = (unsigned long long*)ctx->d_small.p;
     cudaError_t e = cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t*)ctx->d_in.p + n, 0, 16, ctx->stream);  // last word past n
     if (e != cudaSuccess) { st = fail(ctx, e, "upload"); break; }
     timer_begin(ctx);
     // every allocated row gets its closed-form value, so growing `wrap` later is free

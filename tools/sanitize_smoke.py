@@ -1,0 +1,40 @@
+"""Small end-to-end pass over every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import sys
+from pathlib import Path
+import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import lightmotif_b200 as lm
+from oracle import oracle as O
+
+z = np.load(Path(__file__).resolve().parent.parent / "tests/golden/jaspar2024.npz")
+pssm = O.pssm_from_counts(O.DNA, z["rest"], 0.1)
+dna = lm.Pipeline.cuda(lm.DNA)
+n = 300_007
+sym = O.synth_dna(n)
+sym[1000:1100] = 4
+ascii_ = np.frombuffer(b"ACTGN", np.uint8)[sym]
+seq = dna.sequence_from_ascii(ascii_, 19)
+st = O.stripe(O.DNA, sym, 32, 19)
+assert np.array_equal(seq.download(), st)
+want = O.score_f32(pssm, st, n)
+assert np.array_equal(seq.score(pssm).view(np.uint32), want.view(np.uint32))
+dna.set_boot_rows(512)
+for fmode in (1, 2):
+    dna.set_prune(2); dna.set_filter_mode(fmode)
+    best = seq.score_argmax(pssm)
+    r, c = O.argmax(want, O.RULE_AVX2)
+    assert (best["row"], best["col"]) == (r, c), (fmode, best, r, c)
+    assert dna.last_stats["pruned"]
+    hits = seq.score_threshold(pssm, 8.0)
+    ro, co = O.threshold(want, 8.0)
+    assert [(h["row"], h["col"]) for h in hits] == list(zip(ro.tolist(), co.tolist()))
+dna.set_prune(0)
+assert seq.score_argmax(pssm)["position"] == best["position"]
+dm = O.Discrete(O.DNA, pssm)
+u8 = seq.score(dm.data) if False else None
+enc = dna.encode(ascii_)
+assert np.array_equal(enc, sym)
+striped = dna.stripe(sym, 19)
+assert np.array_equal(striped, st)
+print("sanitize smoke ok", best)

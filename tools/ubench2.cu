@@ -68,6 +68,34 @@ __global__ void k_dp2a(int iters, unsigned tl, unsigned th, unsigned w, unsigned
   EPILOG(s)
 }
 
+// Table look-ups with per-lane indices that change every step (nothing can be hoisted):
+// MODE 0: LDS.32   1: LDC (constant bank, indexed)   2: one LDS + one LDC per step   3: index update only
+__constant__ float ctab[64 * 8];
+template <int MODE>
+__global__ void k_lookup(int iters, int ndist, unsigned* out, Res* res) {
+  __shared__ float stab[64 * 8];
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) stab[i] = i * 0.001f;
+  unsigned idx[ILP]; float acc[ILP];
+  for (int i = 0; i < ILP; i++) { idx[i] = (threadIdx.x * 7 + i * 3 + (threadIdx.x >> 3)) % ndist; acc[i] = 0.f; }
+  PROLOG
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int i = 0; i < ILP; i++) {
+        // next symbol: cheap LCG step folded into 0..7, kept < ndist by the caller's choice of 4/8
+        idx[i] = (idx[i] * 5u + 1u) & (unsigned)(ndist - 1);
+        const unsigned a = idx[i] + (u * ILP + i) % 8 * 8;   // row * 8 + symbol
+        if (MODE == 0) acc[i] += stab[a];
+        else if (MODE == 1) acc[i] += ctab[a];
+        else if (MODE == 2) acc[i] += ((i & 1) ? stab[a] : ctab[a]);
+        else acc[i] += __uint_as_float(a);
+      }
+  }
+  float s = 0; for (int i = 0; i < ILP; i++) s += acc[i];
+  EPILOG(__float_as_uint(s))
+}
+
 template <typename F>
 void run(const char* name, int threads, int bps, int nsm, double ops, int iters, F launch) {
   Res* res; unsigned* out;
@@ -96,6 +124,10 @@ int main() {
     RUN(3, "IMAD only, 1 instr", 1.0)
     RUN(4, "2 PRMT + 1 IMAD + 1 IADD, 2 instr/pair", 2.0)
     RUN(5, "PRMT + IMAD + SHF/8", 2.125)
+    run("lookup LDS.32 (4 symbols)", threads, bps, nsm, OPS, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_lookup<0><<<g, t>>>(it, 4, o, r); });
+    run("lookup LDC indexed (4 symbols)", threads, bps, nsm, OPS, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_lookup<1><<<g, t>>>(it, 4, o, r); });
+    run("lookup LDS + LDC alternating", threads, bps, nsm, OPS, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_lookup<2><<<g, t>>>(it, 4, o, r); });
+    run("index update only", threads, bps, nsm, OPS, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_lookup<3><<<g, t>>>(it, 4, o, r); });
     run("dp2a only, 1 instr", threads, bps, nsm, OPS, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_dp2a<0><<<g, t>>>(it, 0x03020100u, 0x07060504u, 0x00001001u, o, r); });
     run("dp2a + PRMT, 2 instr", threads, bps, nsm, OPS * 2, IT, [&](int g, int t, int it, unsigned* o, Res* r) { k_dp2a<1><<<g, t>>>(it, 0x03020100u, 0x07060504u, 0x00001001u, o, r); });
   }
