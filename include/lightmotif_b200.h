@@ -295,6 +295,17 @@ int lm_seq_score_argmax_f32_batch(lm_ctx *ctx, const lm_seq *seq,
                                   const float *pssms, const uint32_t *widths,
                                   const uint64_t *offsets, size_t n_motifs,
                                   size_t pssm_stride, int rule, lm_hit *best);
+/* Same job loop with one threshold per motif (what the CLI computes from a
+ * p-value, lightmotif-cli/src/main.rs:468-497): hits of motif i go to
+ * hits[i * cap ..] in row-major order, counts[i] = total number of hits of
+ * motif i.  LM_ERR_OVERFLOW if any count exceeds cap (the first `cap` hits of
+ * those motifs are still written).  All scans are enqueued back to back and
+ * the host synchronises once. */
+int lm_seq_score_threshold_f32_batch(lm_ctx *ctx, const lm_seq *seq,
+                                     const float *pssms, const uint32_t *widths,
+                                     const uint64_t *offsets, size_t n_motifs,
+                                     size_t pssm_stride, const float *thresholds,
+                                     lm_hit *hits, size_t cap, size_t *counts);
 
 /* Merge per-column winners of `n_parts` consecutive row slabs (slab p scored
  * rows [row_offsets[p], row_offsets[p+1])) into the cell the single-call

@@ -205,6 +205,36 @@ class DeviceSequence:
         self._pli._check(st)
         return [_hit(hits[i]) for i in range(count.value)]
 
+    def _flatten(self, pssms):
+        k = alphabet_k(self.alphabet)
+        stride = pad_pssm(np.zeros((1, k), np.float32), self.alphabet)[1]
+        widths = np.array([len(p) for p in pssms], dtype=np.uint32)
+        offs = np.zeros(len(pssms), dtype=np.uint64)
+        flat = np.zeros((int(widths.sum()), stride), dtype=np.float32)
+        at = 0
+        for i, p in enumerate(pssms):
+            offs[i] = at * stride
+            flat[at:at + len(p), :k] = np.asarray(p, dtype=np.float32)
+            at += len(p)
+        return flat, widths, offs, stride
+
+    def score_threshold_batch(self, pssms, thresholds, cap=4096, counts_only=False):
+        """Many motifs, one threshold each (lm_seq_score_threshold_f32_batch) -> list of hit lists
+        (or, with counts_only, just the number of hits per motif)."""
+        flat, widths, offs, stride = self._flatten(pssms)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float32)
+        assert thr.size == len(pssms)
+        hits = (Hit * (len(pssms) * cap))()
+        counts = (C.c_size_t * len(pssms))()
+        st = capi.lib().lm_seq_score_threshold_f32_batch(self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs),
+                                                         len(pssms), stride, _ptr(thr), hits, cap, counts)
+        if counts_only and st in (capi.OK, capi.ERR_OVERFLOW):
+            return [int(c) for c in counts]
+        if st == capi.ERR_OVERFLOW:
+            return self.score_threshold_batch(pssms, thresholds, cap=max(counts))
+        self._pli._check(st)
+        return [[_hit(hits[q * cap + i]) for i in range(counts[q])] for q in range(len(pssms))]
+
     def score_argmax_batch(self, pssms, rule=RULE_AVX2):
         """Many motifs over this sequence (the lightmotif-cli job loop)."""
         k = alphabet_k(self.alphabet)
@@ -349,7 +379,7 @@ class Pipeline:
     def last_stats(self):
         out = (C.c_uint64 * 4)()
         self._check(capi.lib().lm_ctx_last_stats(self._ctx, C.byref(out)))
-        return {"rechecked": int(out[0]), "overflow_tiles": int(out[1]), "pruned": bool(out[2]),
+        return {"rechecked": int(out[0]), "overflow_tiles": int(out[1]), "pruned": int(out[2]),  # 1 if the filter ran (batch calls: number of motifs that ran it)
                 "filter_rows": int(out[3]) & 0xff, "paired": bool(int(out[3]) >> 8)}
 
     # ---- Encode ---------------------------------------------------------

@@ -50,7 +50,7 @@ SYMBOLS = [
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
-    "lm_seq_score_argmax_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
+    "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
 ]
 
 
@@ -122,6 +122,7 @@ def _declare(L):
     L.lm_seq_score_argmax_f32_finish.argtypes = [vp, i, i, hitp, cwp, f32p]
     L.lm_seq_score_threshold_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, C.c_float, hitp, sz, szp]
     L.lm_seq_score_argmax_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, hitp]
+    L.lm_seq_score_threshold_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp, hitp, sz, vp]
     L.lm_argmax_merge.argtypes = [cwp, sz, vp, C.c_float, C.c_uint64, i, hitp]
     L.lm_ctx_result_block.argtypes = [vp, i]
     L.lm_ctx_result_block.restype = vp

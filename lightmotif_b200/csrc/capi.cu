@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -1117,6 +1118,91 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
   return fetch_hits(ctx, hits, cap, count);
 }
 
+// ---- many motifs over one resident sequence (the lightmotif-cli job loop).  Every motif is
+// planned on the host; motifs with a profitable filter run the filter + recheck kernel, the others
+// the exact kernel.  All kernels of the batch are enqueued back to back -- each with its own 512-byte
+// result block and its own tables -- and the host synchronises ONCE at the end.
+namespace {
+
+struct BatchItem {
+  size_t m = 0;
+  bool pruned = false;
+  PrunePlan plan;
+  size_t tab16_off = 0, tab8_off = 0;  // byte offsets into the staged table buffer
+};
+
+constexpr size_t BATCH_BLOCK = 512;  // bytes of device scratch per motif (SmallBlock layout)
+
+// plan every motif and stage all tables with one H2D copy; returns device base pointers
+int batch_stage(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths, const uint64_t* offsets,
+                size_t n_motifs, size_t pssm_stride, bool argmax_mode, const float* thresholds, size_t n_rows,
+                std::vector<BatchItem>& items, size_t* max_m_out) {
+  const int alphabet = seq->alphabet;
+  const int kp = table_kp(alphabet);
+  items.assign(n_motifs, BatchItem());
+  size_t bytes = 0, max_m = 0;
+  const double npos = (double)n_rows * 32.0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    items[q].m = widths[q];
+    if (widths[q] == 0) return LM_ERR_INVALID_ARG;
+  }
+  // planning is ~0.5 ms of host work per motif: spread it over the host cores
+  if (ctx->opt_prune && alphabet == LM_DNA && n_rows > 16384) {
+    const int opt_prune = ctx->opt_prune, force_r = ctx->opt_filter_rows, force_mode = ctx->opt_filter_mode;
+    const size_t length = seq->length;
+    auto plan_range = [&](size_t q0, size_t q1) {
+      for (size_t q = q0; q < q1; ++q) {
+        BatchItem& it = items[q];
+        if (length < it.m) continue;
+        const float* p = pssms + offsets[q];
+        it.plan = argmax_mode ? plan_prune(p, it.m, pssm_stride, estimate_max_score(p, it.m, pssm_stride, npos), true,
+                                           npos, force_r, force_mode)
+                              : plan_prune(p, it.m, pssm_stride, (double)thresholds[q], false, npos, force_r, force_mode);
+        if (opt_prune == 2 && it.plan.r > 0) it.plan.ok = true;
+        it.pruned = it.plan.ok;
+      }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t n_threads = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, n_motifs / 8}));
+    if (n_threads <= 1) {
+      plan_range(0, n_motifs);
+    } else {
+      std::vector<std::thread> pool;
+      for (size_t t = 0; t < n_threads; ++t)
+        pool.emplace_back(plan_range, n_motifs * t / n_threads, n_motifs * (t + 1) / n_threads);
+      for (auto& th : pool) th.join();
+    }
+  }
+  for (size_t q = 0; q < n_motifs; ++q) {
+    BatchItem& it = items[q];
+    max_m = std::max(max_m, it.m);
+    it.tab16_off = bytes;
+    bytes += (size_t)table_mpad(it.m) * kp * 4;
+    it.tab8_off = bytes;
+    if (it.pruned) bytes += (size_t)table_mpad(it.m) * 8 * 4;
+  }
+  *max_m_out = max_m;
+  LM_CHECK(ensure_pinned(ctx, bytes + 64));
+  LM_CHECK(ensure(ctx, ctx->d_table, bytes + 64));
+  ctx->table_key.clear();  // d_table now holds the batch, not a single matrix
+  uint8_t* h = (uint8_t*)ctx->h_pin;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    const BatchItem& it = items[q];
+    const float* p = pssms + offsets[q];
+    build_table_f32(alphabet, p, it.m, pssm_stride, (uint32_t*)(h + it.tab16_off));
+    if (it.pruned) {
+      float* t8 = (float*)(h + it.tab8_off);
+      std::memset(t8, 0, (size_t)table_mpad(it.m) * 8 * 4);
+      for (size_t j = 0; j < it.m; ++j)
+        for (int a = 0; a < 5; ++a) t8[j * 8 + a] = p[j * pssm_stride + a];
+    }
+  }
+  LM_TRY(cudaMemcpyAsync(ctx->d_table.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return LM_OK;
+}
+
+}  // namespace
+
 int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
                                   const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int rule,
                                   lm_hit* best) {
@@ -1127,72 +1213,170 @@ int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* p
   if (n_motifs == 0) return LM_OK;
   if (n_motifs > 65536) return LM_ERR_UNSUPPORTED;
   const int alphabet = seq->alphabet;
-  const int kp = table_kp(alphabet);
-  size_t max_m = 0, total_words = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    if (widths[q] == 0) return LM_ERR_INVALID_ARG;
-    max_m = std::max<size_t>(max_m, widths[q]);
-    total_words += (size_t)table_mpad(widths[q]) * kp;
-  }
-  int st = check_score_args(max_m, seq->rows, seq->wrap, seq->length, 0, seq->rows);
+  const size_t n_rows = seq->rows;
+  std::vector<BatchItem> items;
+  size_t max_m = 0;
+  for (size_t q = 0; q < n_motifs; ++q) max_m = std::max<size_t>(max_m, widths[q]);
+  int st = check_score_args(max_m ? max_m : 1, seq->rows, seq->wrap, std::max(seq->length, max_m), 0, seq->rows);
   if (st < 0) return st;
   LM_CHECK(limits_ok(alphabet, max_m));
-  // host staging: [tables | table_off u64 | m_pads i32]
-  const size_t tab_bytes = total_words * 4;
-  const size_t off_bytes = n_motifs * 8, mp_bytes = n_motifs * 4;
-  const size_t stage_bytes = tab_bytes + off_bytes + mp_bytes + 64;
-  LM_CHECK(ensure_pinned(ctx, stage_bytes));
-  LM_CHECK(ensure(ctx, ctx->d_table, stage_bytes));
-  ctx->table_key.clear();  // d_table now holds the batch, not a single matrix
-  uint8_t* h = (uint8_t*)ctx->h_pin;
-  uint32_t* h_tab = (uint32_t*)h;
-  size_t off_at = (tab_bytes + 15) & ~(size_t)15;
-  uint64_t* h_off = (uint64_t*)(h + off_at);
-  int* h_mp = (int*)(h + off_at + off_bytes);
-  size_t w = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    h_off[q] = w;
-    h_mp[q] = table_mpad(widths[q]);
-    build_table_f32(alphabet, pssms + offsets[q], widths[q], pssm_stride, h_tab + w);
-    w += (size_t)h_mp[q] * kp;
-  }
-  LM_TRY(cudaMemcpyAsync(ctx->d_table.p, h, off_at + off_bytes + mp_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t key_bytes = n_motifs * 32 * 8, fc_bytes = n_motifs * 4;
-  LM_CHECK(ensure(ctx, ctx->d_out, key_bytes + fc_bytes));
-  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, key_bytes + fc_bytes, ctx->stream));
-  // motifs shorter than the sequence's length are all scorable; a motif longer
-  // than the sequence yields LM_EMPTY semantics (position = 0, valid = 0)
-  ScoreArgs a;
-  a.seq = seq->data;
-  a.avail_rows = seq->alloc_rows;
-  a.row_begin = 0;
-  a.row_end = seq->rows;
-  a.pad_sym = pad_symbol(alphabet);
-  uint8_t* d = (uint8_t*)ctx->d_table.p;
-  a.tables = (const uint32_t*)d;
-  a.table_off = (const uint64_t*)(d + off_at);
-  a.m_pads = (const int*)(d + off_at + off_bytes);
-  a.m_pad = table_mpad(max_m);
-  a.n_motifs = (int)n_motifs;
-  a.colkeys = (unsigned long long*)ctx->d_out.p;
-  a.first_cell = (uint32_t*)((uint8_t*)ctx->d_out.p + key_bytes);
+  LM_CHECK(batch_stage(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, true, nullptr, n_rows, items, &max_m));
+  LM_CHECK(ensure(ctx, ctx->d_out, n_motifs * BATCH_BLOCK));
+  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, n_motifs * BATCH_BLOCK, ctx->stream));
+  const int sms = std::max(1, ctx->sm_count - ctx->opt_reserve_sms);
+  // rows scored exactly first to seed each filtered scan's running maximum
+  const size_t boot = std::min<size_t>(ctx->opt_boot_rows, std::max<size_t>(8192, n_rows / 32));
   timer_begin(ctx);
-  LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, ctx->sm_count, ctx->stream));
-  timer_end(ctx);
-  ctx->launches += 1;
-  std::vector<unsigned long long> keys(n_motifs * 32);
-  std::vector<uint32_t> fc(n_motifs);
-  LM_TRY(cudaMemcpyAsync(keys.data(), a.colkeys, key_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  LM_TRY(cudaMemcpyAsync(fc.data(), a.first_cell, fc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  uint64_t n_pruned = 0, launches = 0;
   for (size_t q = 0; q < n_motifs; ++q) {
+    const BatchItem& it = items[q];
+    if (seq->length < it.m) continue;  // nothing to score: best[q] stays zeroed
+    uint8_t* block = (uint8_t*)ctx->d_out.p + q * BATCH_BLOCK;
+    ScoreArgs a;
+    a.seq = seq->data;
+    a.avail_rows = seq->alloc_rows;
+    a.row_begin = 0;
+    a.row_end = it.pruned ? std::min(boot, n_rows) : n_rows;
+    a.pad_sym = pad_symbol(alphabet);
+    a.tables = (const uint32_t*)((uint8_t*)ctx->d_table.p + it.tab16_off);
+    a.m_pad = table_mpad(it.m);
+    a.n_motifs = 1;
+    a.colkeys = (unsigned long long*)block;
+    a.first_cell = (uint32_t*)(block + 256);
+    LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, sms, ctx->stream));
+    ++launches;
+    if (it.pruned && n_rows > boot) {
+      PruneArgs pa;
+      pa.seq = seq->data;
+      pa.avail_rows = seq->alloc_rows;
+      pa.row_begin = 0;
+      pa.row_first = boot;
+      pa.row_end = n_rows;
+      pa.pad_sym = pad_symbol(alphabet);
+      pa.table = (const float*)((uint8_t*)ctx->d_table.p + it.tab8_off);
+      pa.plan = it.plan;
+      pa.colkeys = (unsigned long long*)block;
+      pa.stats = (unsigned long long*)(block + 272);
+      LM_TRY(launch_prune(false, pa, sms, ctx->stream));
+      ++launches;
+      ++n_pruned;
+    }
+  }
+  timer_end(ctx);
+  ctx->launches += launches;
+  std::vector<uint8_t> blocks(n_motifs * BATCH_BLOCK);
+  LM_TRY(cudaMemcpyAsync(blocks.data(), ctx->d_out.p, blocks.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  uint64_t cand = 0, over = 0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    const SmallBlock* sb = (const SmallBlock*)(blocks.data() + q * BATCH_BLOCK);
     lm_colwin cw[32];
-    decode_colwins(&keys[q * 32], false, cw);
+    decode_colwins(sb->ck.keys, false, cw);
     std::memset(&best[q], 0, sizeof(lm_hit));
     if (seq->length < widths[q]) continue;
-    apply_rule(cw, bits_to_score(fc[q], false), rule, false, seq->rows, 0, &best[q]);
+    apply_rule(cw, bits_to_score(sb->ck.first_cell, false), rule, false, seq->rows, 0, &best[q]);
+    cand += sb->stats[0];
+    over += sb->stats[1];
   }
+  ctx->stats[0] = cand;
+  ctx->stats[1] = over;
+  ctx->stats[2] = n_pruned;  // number of motifs that ran the filter
+  ctx->stats[3] = 0;
   return LM_OK;
+}
+
+int lm_seq_score_threshold_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                     const uint64_t* offsets, size_t n_motifs, size_t pssm_stride,
+                                     const float* thresholds, lm_hit* hits, size_t cap, size_t* counts) {
+  LM_CHECK(bind(ctx));
+  if (!seq || !pssms || !widths || !offsets || !thresholds || !counts || (cap && !hits) ||
+      pssm_stride < (size_t)alphabet_k(seq->alphabet))
+    return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  for (size_t q = 0; q < n_motifs; ++q) counts[q] = 0;
+  if (n_motifs == 0) return LM_OK;
+  if (n_motifs > 65536) return LM_ERR_UNSUPPORTED;
+  const int alphabet = seq->alphabet;
+  const size_t n_rows = seq->rows;
+  size_t max_m = 0;
+  for (size_t q = 0; q < n_motifs; ++q) max_m = std::max<size_t>(max_m, widths[q]);
+  int st = check_score_args(max_m ? max_m : 1, seq->rows, seq->wrap, std::max(seq->length, max_m), 0, seq->rows);
+  if (st < 0) return st;
+  LM_CHECK(limits_ok(alphabet, max_m));
+  std::vector<BatchItem> items;
+  LM_CHECK(batch_stage(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, false, thresholds, n_rows, items, &max_m));
+  LM_CHECK(ensure(ctx, ctx->d_out, n_motifs * BATCH_BLOCK));
+  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(n_motifs * cap, 1) * sizeof(lm_hit)));
+  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, n_motifs * BATCH_BLOCK, ctx->stream));
+  const int sms = std::max(1, ctx->sm_count - ctx->opt_reserve_sms);
+  timer_begin(ctx);
+  uint64_t n_pruned = 0, launches = 0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    const BatchItem& it = items[q];
+    if (seq->length < it.m) continue;
+    uint8_t* block = (uint8_t*)ctx->d_out.p + q * BATCH_BLOCK;
+    lm_hit* d_hits = (lm_hit*)ctx->d_hits.p + q * cap;
+    if (it.pruned) {
+      PruneArgs pa;
+      pa.seq = seq->data;
+      pa.avail_rows = seq->alloc_rows;
+      pa.row_begin = 0;
+      pa.row_first = 0;
+      pa.row_end = n_rows;
+      pa.pad_sym = pad_symbol(alphabet);
+      pa.table = (const float*)((uint8_t*)ctx->d_table.p + it.tab8_off);
+      pa.plan = it.plan;
+      pa.thr = thresholds[q];
+      pa.hits = d_hits;
+      pa.cap = cap;
+      pa.count = (unsigned long long*)(block + 264);
+      pa.stats = (unsigned long long*)(block + 272);
+      LM_TRY(launch_prune(true, pa, sms, ctx->stream));
+      ++n_pruned;
+    } else {
+      ScoreArgs a;
+      a.seq = seq->data;
+      a.avail_rows = seq->alloc_rows;
+      a.row_begin = 0;
+      a.row_end = n_rows;
+      a.pad_sym = pad_symbol(alphabet);
+      a.tables = (const uint32_t*)((uint8_t*)ctx->d_table.p + it.tab16_off);
+      a.m_pad = table_mpad(it.m);
+      a.n_motifs = 1;
+      a.colkeys = (unsigned long long*)block;
+      a.first_cell = (uint32_t*)(block + 256);
+      a.count = (unsigned long long*)(block + 264);
+      std::memcpy(&a.thr_bits, &thresholds[q], 4);
+      a.hits = d_hits;
+      a.cap = cap;
+      LM_TRY(launch_score(alphabet, MODE_THRESHOLD, false, a, sms, ctx->stream));
+    }
+    ++launches;
+  }
+  timer_end(ctx);
+  ctx->launches += launches;
+  std::vector<uint8_t> blocks(n_motifs * BATCH_BLOCK);
+  LM_TRY(cudaMemcpyAsync(blocks.data(), ctx->d_out.p, blocks.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  bool overflow = false;
+  uint64_t cand = 0, over = 0;
+  for (size_t q = 0; q < n_motifs; ++q) {
+    const SmallBlock* sb = (const SmallBlock*)(blocks.data() + q * BATCH_BLOCK);
+    counts[q] = (size_t)sb->count;
+    cand += sb->stats[0];
+    over += sb->stats[1];
+    const size_t n = std::min<size_t>(counts[q], cap);
+    overflow = overflow || counts[q] > cap;
+    if (n) LM_TRY(cudaMemcpyAsync(hits + q * cap, (lm_hit*)ctx->d_hits.p + q * cap, n * sizeof(lm_hit),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  for (size_t q = 0; q < n_motifs; ++q) sort_hits(hits + q * cap, std::min<size_t>(counts[q], cap));
+  ctx->stats[0] = cand;
+  ctx->stats[1] = over;
+  ctx->stats[2] = n_pruned;
+  ctx->stats[3] = 0;
+  return overflow ? LM_ERR_OVERFLOW : LM_OK;
 }
 
 int lm_argmax_merge(const lm_colwin* parts, size_t n_parts, const uint64_t* row_offsets, float first_cell,

@@ -351,6 +351,31 @@ def test_batch_argmax(dna, jaspar):
         assert (single["row"], single["col"]) == (r, c)
 
 
+def test_batch_through_filter(dna, jaspar):
+    """The many-motif job loop with per-motif planning: motifs with a profitable filter run the
+    filter + recheck kernel, the rest the exact kernel; results == one exact call per motif, for
+    argmax and for per-motif thresholds (hits in row-major order, exact scores)."""
+    n = 6_000_000
+    motifs = [m for m in jaspar["motifs"] if 6 <= len(m) <= 30][:40] + [jaspar["rest"]]
+    pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in motifs]
+    maxw = max(len(p) for p in pssms)
+    seq = dna.sequence_synthetic(n, maxw - 1)
+    dna.set_prune(0)
+    want_best = [seq.score_argmax(p) for p in pssms]
+    thr = [float(np.float32(b["score"] - 2.5)) for b in want_best]
+    want_hits = [seq.score_threshold(p, t) for p, t in zip(pssms, thr)]
+    for mode in (1, 2):
+        dna.set_prune(mode)
+        got = seq.score_argmax_batch(pssms)
+        assert dna.last_stats["pruned"] >= 1  # stats[2] = number of motifs that ran the filter
+        for g, w in zip(got, want_best):
+            assert (g["row"], g["col"], g["position"]) == (w["row"], w["col"], w["position"])
+            assert bits(np.float32(g["score"])) == bits(np.float32(w["score"]))
+        hits = seq.score_threshold_batch(pssms, thr, cap=64)  # small cap: exercises the overflow retry
+        assert hits == want_hits
+    dna.set_prune(1)
+
+
 def test_sharded_merge_equals_single_call(lm, dna, jaspar):
     """Row slabs scored independently + lm_argmax_merge == one call (the
     multi-GPU reduction, exercised on one device)."""

@@ -75,8 +75,25 @@ def main():
                                   "gadds_s": adds / b / 1e6,
                                   "fp32_add_ceiling_gadds_s": 148 * 128 * 1.965,
                                   "lds_ceiling_glookups_s": 148 * 32 * 1.965,
-                                  "note": "exact per-cell f32 sums (score_kernel, n_motifs > 1): bound by the shared-memory "
-                                          "look-up pipe (1 LDS per cell update)"}
+                                  "note": "per-motif planning: filter + recheck kernel where profitable, exact per-cell f32 "
+                                          "sums otherwise (bound by the shared-memory look-up pipe, 1 LDS per cell update)"}
+    out["config2_many_motifs"]["motifs_through_filter"] = int(dna.last_stats["pruned"])
+    t0 = time.perf_counter()
+    seq.score_argmax_batch(pssms)
+    out["config2_many_motifs"]["call_s_wall"] = time.perf_counter() - t0
+    dna.set_prune(0)
+    b0, _, res0 = best_ms(lambda: seq.score_argmax_batch(pssms), dna, 1)
+    dna.set_prune(1)
+    out["config2_many_motifs"]["exact_only_kernel_ms"] = b0
+    assert [(r["position"], r["score"]) for r in res0] == [(r["position"], r["score"]) for r in res]
+    # per-motif thresholds 3 bits below each motif's maximum (the CLI's p-value cut-offs, roughly)
+    thr = [float(np.float32(r["score"] - 3.0)) for r in res]
+    seq.score_threshold_batch(pssms, thr, cap=1 << 14, counts_only=True)
+    t0 = time.perf_counter()
+    counts = seq.score_threshold_batch(pssms, thr, cap=1 << 14, counts_only=True)
+    out["config2_many_motifs"]["threshold_batch"] = {"kernel_ms": dna.last_kernel_ms, "call_s_wall": time.perf_counter() - t0,
+                                                     "hits": int(sum(counts)), "thresholds": "per-motif maximum - 3.0",
+                                                     "motifs_through_filter": int(dna.last_stats["pruned"])}
     # spot check 3 motifs against single calls
     for i in (0, len(pssms) // 2, len(pssms) - 1):
         single = seq.score_argmax(pssms[i])
