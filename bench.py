@@ -224,26 +224,31 @@ def run_ours(args):
 
     # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners: an NCCL
     # all-gather of the 272-byte result block straight from HBM, enqueued on the scan's stream, and
-    # the tie-rule merge on the host.  Steps are software-pipelined one deep: scan k+1 is enqueued
-    # before the host waits for scan k.
+    # the tie-rule merge on the host.  Steps are software-pipelined `depth` deep: scans k+1 .. k+depth
+    # are enqueued before the host waits for scan k (so a late rank or a slow host thread does not
+    # idle the other GPUs).
+    NSLOT = 4
+    depth = args.depth  # scans enqueued ahead of the one the host waits for (< NSLOT)
+
     def launch(k):
-        seq.score_argmax_launch(pssm, slot=k & 1)
+        seq.score_argmax_launch(pssm, slot=k % NSLOT)
         if world > 1:
-            xchg.enqueue(pli.result_block_ptr(k & 1), slot=k & 1)
+            xchg.enqueue(pli.result_block_ptr(k % NSLOT), slot=k % NSLOT)
 
     def finish(k):
-        res = seq.score_argmax_finish(slot=k & 1, rule=lm.RULE_AVX2)
+        res = seq.score_argmax_finish(slot=k % NSLOT, rule=lm.RULE_AVX2)
         kms = pli.last_kernel_ms
         if world > 1:  # global argmax over all slabs (every rank computes the same cell)
-            res = xchg.finish(k & 1, row_offsets, rows_global, lm.RULE_AVX2)
+            res = xchg.finish(k % NSLOT, row_offsets, rows_global, lm.RULE_AVX2)
         return res, kms
 
     def run_steps(n, sampler=None):
         out = []
-        launch(0)
+        for j in range(min(depth, n)):
+            launch(j)
         for k in range(n):
-            if k + 1 < n:
-                launch(k + 1)
+            if k + depth < n:
+                launch(k + depth)
             if sampler is not None and world == 1 and n >= 4 and k in (n // 4, n // 2, (3 * n) // 4):
                 sampler.sample_nvml()  # the GPU is busy with scans k and k + 1 here
             out.append(finish(k))
@@ -391,6 +396,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, choices=[1, 2, 3], help="scans enqueued ahead of the host")
     ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs the scan grid leaves free for the NCCL kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -260,10 +260,11 @@ int lm_seq_score_argmax_f32(lm_ctx *ctx, const lm_seq *seq, const float *pssm,
                             size_t row_end, int rule, lm_hit *best,
                             lm_colwin *per_column, float *first_cell);
 /* Split form of lm_seq_score_argmax_f32 for pipelining: `launch` only enqueues
- * the kernels and the copy of the 300-byte result block (slot = 0 or 1, so two
- * calls can be in flight: e.g. the scan of motif k+1 runs while the host merges
+ * the kernels and the copy of the small result block (0 <= slot < LM_SLOTS, so
+ * several calls can be in flight: e.g. the scan of motif k+1 runs while the host merges
  * / all-gathers the winners of motif k); `finish` waits for that slot and
  * returns exactly what the one-shot call returns. */
+#define LM_SLOTS 4
 int lm_seq_score_argmax_f32_launch(lm_ctx *ctx, const lm_seq *seq,
                                    const float *pssm, size_t m,
                                    size_t pssm_stride, size_t row_begin,
@@ -306,6 +307,36 @@ int lm_seq_score_threshold_f32_batch(lm_ctx *ctx, const lm_seq *seq,
                                      const uint64_t *offsets, size_t n_motifs,
                                      size_t pssm_stride, const float *thresholds,
                                      lm_hit *hits, size_t cap, size_t *counts);
+
+/* The filter the fused DNA calls would use for `pssm` (host only, no GPU
+ * needed): introspection for tests and tuning.  The kernel computes, per
+ * position p, sum_q(p) = sum over look-ups k < r of table_k[entry_k(p)] with
+ *   single mode (pair == 0): entry_k = symbol at motif row j0 + k
+ *                            (table = tab_lo bytes A,C,T,G | tab_hi byte 0 = N);
+ *   paired mode:             entry_k = s | class(s') << 2, s / s' = symbols at
+ *                            rows j0 + 2k / j0 + 2k + 1, class(x) = bit 2 of
+ *                            x * pair_mul, N as first symbol = entry 4
+ *                            (entries 0..3 = tab_lo bytes, 4..7 = tab_hi bytes);
+ * and guarantees  c0 + delta * sum_q(p) >= score(p)  in real arithmetic, with
+ * |f32 sequential score - real score| <= eps.  A position is rechecked exactly
+ * iff sum_q(p) >= ceil((T - eps - c0) / delta) - 1 for the current threshold T.
+ * `threshold` is the planning threshold (is_argmax != 0: ignored, the expected
+ * maximum over n_positions uniform-random positions is used). */
+typedef struct lm_filter_plan {
+  int ok;       /* 1 if the cost model prefers the filter over exact scoring */
+  int r;        /* look-ups per position */
+  int pair;     /* 0 single rows, 1 paired rows */
+  uint32_t pair_mul;
+  int j0;
+  int smax;     /* largest attainable sum_q (<= 127) */
+  uint32_t tab_lo[16], tab_hi[16];
+  double c0, delta, eps;
+  double est_pass_rate; /* under a uniform ACGT background at the planning threshold */
+  double est_cost;      /* modelled issue slots per 128 positions */
+} lm_filter_plan;
+int lm_plan_filter(const float *pssm, size_t m, size_t pssm_stride,
+                   double threshold, int is_argmax, double n_positions,
+                   int force_lookups, int force_mode, lm_filter_plan *out);
 
 /* Merge per-column winners of `n_parts` consecutive row slabs (slab p scored
  * rows [row_offsets[p], row_offsets[p+1])) into the cell the single-call

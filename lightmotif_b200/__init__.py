@@ -517,6 +517,20 @@ def f32_key(x):
     return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
 
 
+def plan_filter(pssm, threshold=None, n_positions=5e9, lookups=0, mode=0):
+    """lm_plan_filter: the filter the fused DNA calls would use (host only).  threshold=None plans
+    for an argmax scan over n_positions.  Returns a dict, or None when no filter exists."""
+    p, stride = pad_pssm(pssm, DNA)
+    out = capi.FilterPlan()
+    st = capi.lib().lm_plan_filter(_ptr(p), p.shape[0], stride, 0.0 if threshold is None else float(threshold),
+                                   1 if threshold is None else 0, float(n_positions), int(lookups), int(mode), C.byref(out))
+    if st != capi.OK:
+        return None
+    return {"ok": bool(out.ok), "r": out.r, "pair": bool(out.pair), "pair_mul": out.pair_mul, "j0": out.j0,
+            "smax": out.smax, "tab_lo": list(out.tab_lo), "tab_hi": list(out.tab_hi), "c0": out.c0,
+            "delta": out.delta, "eps": out.eps, "est_pass_rate": out.est_pass_rate, "est_cost": out.est_cost}
+
+
 RESULT_BLOCK_WORDS = 34  # uint64 words of a result block: 32 column keys, first_cell, padding
 
 

@@ -30,6 +30,12 @@ class ColWin(C.Structure):
     _fields_ = [("row", C.c_uint64), ("score", C.c_float), ("valid", C.c_uint32)]
 
 
+class FilterPlan(C.Structure):
+    _fields_ = [("ok", C.c_int), ("r", C.c_int), ("pair", C.c_int), ("pair_mul", C.c_uint32), ("j0", C.c_int),
+                ("smax", C.c_int), ("tab_lo", C.c_uint32 * 16), ("tab_hi", C.c_uint32 * 16), ("c0", C.c_double),
+                ("delta", C.c_double), ("eps", C.c_double), ("est_pass_rate", C.c_double), ("est_cost", C.c_double)]
+
+
 class LightmotifError(RuntimeError):
     def __init__(self, status, detail=""):
         self.status = status
@@ -128,6 +134,7 @@ def _declare(L):
     L.lm_ctx_result_block.restype = vp
     L.lm_decode_keys.argtypes = [vp, cwp]
     L.lm_decode_keys.restype = None
+    L.lm_plan_filter.argtypes = [vp, sz, sz, C.c_double, i, C.c_double, i, i, C.POINTER(FilterPlan)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("lm_abi_version",):

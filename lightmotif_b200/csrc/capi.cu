@@ -48,7 +48,7 @@ struct lm_ctx {
   // host-side set-up once
   std::vector<uint8_t> table_key, table8_key, plan_key;
   PrunePlan plan_cache;
-  // in-flight fused argmax calls (launch / finish split, 2 slots): result blocks
+  // in-flight fused argmax calls (launch / finish split, LM_SLOTS slots): result blocks
   // live at d_small + slot * 1024 and are copied to pinned host memory
   struct Slot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
@@ -57,7 +57,7 @@ struct lm_ctx {
     size_t n_rows = 0;
     bool pruned = false;
     int r = 0;
-  } slots[2];
+  } slots[LM_SLOTS];
   void* h_pin = nullptr;                          // pinned host staging
   size_t h_pin_bytes = 0;
 };
@@ -972,7 +972,7 @@ int lm_seq_score_u8(lm_ctx* ctx, const lm_seq* seq, const uint8_t* dm, size_t m,
 int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m,
                                    size_t pssm_stride, size_t row_begin, size_t row_end, int slot) {
   LM_CHECK(bind(ctx));
-  if (!seq || !pssm || slot < 0 || slot > 1 || pssm_stride < (size_t)alphabet_k(seq->alphabet))
+  if (!seq || !pssm || slot < 0 || slot >= LM_SLOTS || pssm_stride < (size_t)alphabet_k(seq->alphabet))
     return LM_ERR_INVALID_ARG;
   if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
   lm_ctx::Slot& sl = ctx->slots[slot];
@@ -1029,7 +1029,7 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
 int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best, lm_colwin* per_column,
                                    float* first_cell) {
   LM_CHECK(bind(ctx));
-  if (!best || slot < 0 || slot > 1) return LM_ERR_INVALID_ARG;
+  if (!best || slot < 0 || slot >= LM_SLOTS) return LM_ERR_INVALID_ARG;
   lm_ctx::Slot& sl = ctx->slots[slot];
   if (per_column) std::memset(per_column, 0, 32 * sizeof(lm_colwin));
   if (sl.state == 0) return LM_ERR_INVALID_ARG;
@@ -1053,7 +1053,7 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
 }
 
 void* lm_ctx_result_block(lm_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot > 1 || !ctx->d_small.p) return nullptr;
+  if (!ctx || slot < 0 || slot >= LM_SLOTS || !ctx->d_small.p) return nullptr;
   return (uint8_t*)ctx->d_small.p + (size_t)slot * 1024;
 }
 
@@ -1377,6 +1377,27 @@ int lm_seq_score_threshold_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float
   ctx->stats[2] = n_pruned;
   ctx->stats[3] = 0;
   return overflow ? LM_ERR_OVERFLOW : LM_OK;
+}
+
+int lm_plan_filter(const float* pssm, size_t m, size_t pssm_stride, double threshold, int is_argmax,
+                   double n_positions, int force_lookups, int force_mode, lm_filter_plan* out) {
+  if (!pssm || !out || m == 0 || pssm_stride < 5) return LM_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  const double t = is_argmax ? estimate_max_score(pssm, m, pssm_stride, n_positions) : threshold;
+  const PrunePlan p = plan_prune(pssm, m, pssm_stride, t, is_argmax != 0, n_positions, force_lookups, force_mode);
+  out->ok = p.ok ? 1 : 0;
+  out->r = p.r;
+  out->pair = p.pair;
+  out->pair_mul = p.pair_mul;
+  out->j0 = p.j0;
+  out->smax = p.smax;
+  for (int k = 0; k < 16; ++k) { out->tab_lo[k] = p.tab_lo[k]; out->tab_hi[k] = p.tab_hi[k]; }
+  out->c0 = p.c0;
+  out->delta = p.delta;
+  out->eps = p.eps;
+  out->est_pass_rate = p.est_pass_rate;
+  out->est_cost = p.est_cost;
+  return p.r > 0 ? LM_OK : LM_EMPTY;
 }
 
 int lm_argmax_merge(const lm_colwin* parts, size_t n_parts, const uint64_t* row_offsets, float first_cell,

@@ -105,8 +105,11 @@ __device__ __forceinline__ bool dna_word_fast(uint32_t w, uint32_t& code) {
   return letters == __byte_perm(w, 0u, 0x3120);
 }
 
+#ifndef LM_ST_MINB
+#define LM_ST_MINB 4
+#endif
 template <bool FROM_ASCII>
-__global__ void __launch_bounds__(ST_THREADS) stripe_kernel(const uint8_t* __restrict__ src, uint64_t n,
+__global__ void __launch_bounds__(ST_THREADS, LM_ST_MINB) stripe_kernel(const uint8_t* __restrict__ src, uint64_t n,
                                                             uint64_t rows, uint64_t row0,
                                                             uint64_t out_rows, uint8_t* __restrict__ dst,
                                                             int alphabet, uint8_t pad,

@@ -33,20 +33,20 @@ class WinnerExchange:
     the scan kernels leave in HBM (32 packed per-column winners + the first cell) is all-gathered
     straight from there over NCCL/NVLink on the scan's own stream -- no round trip through host
     memory, no host synchronisation -- and only the gathered blocks (world x 272 bytes) are copied
-    to pinned host memory, where `finish` applies the tie rule with ``lm_argmax_merge``.  Two slots,
-    so the exchange of scan k overlaps scan k + 1.
+    to pinned host memory, where `finish` applies the tie rule with ``lm_argmax_merge``.  Several slots,
+    so the exchange of scan k overlaps the following scans.
 
     With the gloo backend (CPU tests) the blocks are host arrays passed to `enqueue` directly."""
 
-    def __init__(self, device=None, group=None):
+    def __init__(self, device=None, group=None, slots=4):
         from . import RESULT_BLOCK_WORDS
         self.group, self.device = group, device
         self.world = dist.get_world_size(group)
         self.words = RESULT_BLOCK_WORDS
         self.cuda = device is not None and torch.device(device).type == "cuda"
-        self.all = [torch.empty((self.world, self.words), dtype=torch.int64, device=device) for _ in range(2)]
-        self.host = [torch.empty((self.world, self.words), dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
-        self.events = [torch.cuda.Event() for _ in range(2)] if self.cuda else [None, None]
+        self.all = [torch.empty((self.world, self.words), dtype=torch.int64, device=device) for _ in range(slots)]
+        self.host = [torch.empty((self.world, self.words), dtype=torch.int64, pin_memory=self.cuda) for _ in range(slots)]
+        self.events = [torch.cuda.Event() for _ in range(slots)] if self.cuda else [None] * slots
         self.side = torch.cuda.Stream(device=device) if self.cuda else None
         self._views = {}
 
