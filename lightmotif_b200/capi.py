@@ -57,6 +57,7 @@ SYMBOLS = [
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
     "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
+    "lm_plan_filter",
 ]
 
 
