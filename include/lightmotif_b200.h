@@ -337,6 +337,15 @@ typedef struct lm_filter_plan {
 int lm_plan_filter(const float *pssm, size_t m, size_t pssm_stride,
                    double threshold, int is_argmax, double n_positions,
                    int force_lookups, int force_mode, lm_filter_plan *out);
+/* Protein flavour: the 21 residues are partitioned into 8 classes chosen for
+ * this matrix (class_of[a], a = residue code 0..20, X = 20); the filter runs on
+ * a class-coded copy of the sequence with single-row look-ups,
+ * entry_k = class of the residue at motif row j0 + k (entries 0..3 = tab_lo
+ * bytes, 4..7 = tab_hi bytes), table entry = best weight within the class. */
+int lm_plan_filter_protein(const float *pssm, size_t m, size_t pssm_stride,
+                           double threshold, int is_argmax, double n_positions,
+                           int force_lookups, lm_filter_plan *out,
+                           uint8_t class_of[21]);
 
 /* Merge per-column winners of `n_parts` consecutive row slabs (slab p scored
  * rows [row_offsets[p], row_offsets[p+1])) into the cell the single-call

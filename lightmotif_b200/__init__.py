@@ -531,6 +531,21 @@ def plan_filter(pssm, threshold=None, n_positions=5e9, lookups=0, mode=0):
             "delta": out.delta, "eps": out.eps, "est_pass_rate": out.est_pass_rate, "est_cost": out.est_cost}
 
 
+def plan_filter_protein(pssm, threshold=None, n_positions=5e8, lookups=0):
+    """lm_plan_filter_protein: class partition + look-up tables the fused protein calls would use."""
+    p, stride = pad_pssm(pssm, PROTEIN)
+    out = capi.FilterPlan()
+    cls = np.zeros(21, dtype=np.uint8)
+    st = capi.lib().lm_plan_filter_protein(_ptr(p), p.shape[0], stride, 0.0 if threshold is None else float(threshold),
+                                           1 if threshold is None else 0, float(n_positions), int(lookups), C.byref(out),
+                                           _ptr(cls))
+    if st != capi.OK:
+        return None
+    return {"ok": bool(out.ok), "r": out.r, "pair": False, "j0": out.j0, "smax": out.smax, "tab_lo": list(out.tab_lo),
+            "tab_hi": list(out.tab_hi), "c0": out.c0, "delta": out.delta, "eps": out.eps,
+            "est_pass_rate": out.est_pass_rate, "est_cost": out.est_cost, "class_of": cls}
+
+
 RESULT_BLOCK_WORDS = 34  # uint64 words of a result block: 32 column keys, first_cell, padding
 
 

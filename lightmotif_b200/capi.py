@@ -57,7 +57,7 @@ SYMBOLS = [
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
     "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
-    "lm_plan_filter",
+    "lm_plan_filter", "lm_plan_filter_protein",
 ]
 
 
@@ -136,6 +136,7 @@ def _declare(L):
     L.lm_decode_keys.argtypes = [vp, cwp]
     L.lm_decode_keys.restype = None
     L.lm_plan_filter.argtypes = [vp, sz, sz, C.c_double, i, C.c_double, i, i, C.POINTER(FilterPlan)]
+    L.lm_plan_filter_protein.argtypes = [vp, sz, sz, C.c_double, i, C.c_double, i, C.POINTER(FilterPlan), vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("lm_abi_version",):

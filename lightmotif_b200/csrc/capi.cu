@@ -36,6 +36,14 @@ struct lm_ctx {
   uint64_t launches = 0;
   char err[256] = {0};
   DevBuf d_in, d_out, d_table, d_table2, d_small, d_hits;  // device scratch, grown on demand
+  // protein filter: class-coded copy of the last sequence scanned (one-entry cache keyed by the
+  // sequence buffer and the residue -> class map)
+  DevBuf d_class;
+  const uint8_t* class_src = nullptr;
+  size_t class_rows = 0;
+  uint8_t class_lut[32] = {0};
+  std::vector<uint8_t> pplan_key;
+  ProteinPlan pplan_cache;
   int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
   int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
   int opt_filter_mode = 0;                // LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single rows, 2 = paired rows
@@ -337,6 +345,52 @@ PrunePlan cached_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, b
   return plan;
 }
 
+// protein: plan with a one-entry cache, recheck table [m_pad][32], class-coded copy of the sequence
+ProteinPlan cached_protein_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, bool argmax_mode, double t,
+                                double npos) {
+  std::vector<uint8_t> key = matrix_key(argmax_mode ? 6 : 7, LM_PROTEIN, pssm, m, stride, 4);
+  double extra[3] = {argmax_mode ? 0.0 : t, npos, (double)ctx->opt_filter_rows};
+  key.insert(key.end(), (const uint8_t*)extra, (const uint8_t*)extra + sizeof(extra));
+  if (key == ctx->pplan_key) return ctx->pplan_cache;
+  ProteinPlan plan = argmax_mode ? plan_prune_protein(pssm, m, stride, estimate_max_score_protein(pssm, m, stride, npos),
+                                                      true, npos, ctx->opt_filter_rows)
+                                 : plan_prune_protein(pssm, m, stride, t, false, npos, ctx->opt_filter_rows);
+  ctx->pplan_key.swap(key);
+  ctx->pplan_cache = plan;
+  return plan;
+}
+
+int upload_table32(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
+  std::vector<uint8_t> key = matrix_key(8, LM_PROTEIN, pssm, m, stride, 4);
+  if (key == ctx->table8_key && ctx->d_table2.p) return LM_OK;
+  ctx->table8_key = key;
+  const size_t m_pad = (m + 3) & ~(size_t)3;
+  const size_t bytes = m_pad * 32 * 4;
+  LM_CHECK(ensure_pinned(ctx, bytes));
+  LM_CHECK(ensure(ctx, ctx->d_table2, bytes));
+  float* h = (float*)ctx->h_pin;
+  std::memset(h, 0, bytes);
+  for (size_t j = 0; j < m; ++j)
+    for (int a = 0; a < 21; ++a) h[j * 32 + a] = pssm[j * stride + a];
+  LM_TRY(cudaMemcpyAsync(ctx->d_table2.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  LM_TRY(cudaStreamSynchronize(ctx->stream));
+  return LM_OK;
+}
+
+int ensure_class_copy(lm_ctx* ctx, const lm_seq* seq, const uint8_t* class_of) {
+  if (seq->owned && ctx->class_src == seq->data && ctx->class_rows == seq->alloc_rows && ctx->d_class.p &&
+      std::memcmp(ctx->class_lut, class_of, 32) == 0)
+    return LM_OK;  // same (library-owned, hence unmodified) sequence, same classes: the copy is still valid
+  LM_CHECK(ensure(ctx, ctx->d_class, seq->alloc_rows * 32));
+  LM_TRY(launch_classmap(seq->data, seq->alloc_rows * 32, (uint8_t*)ctx->d_class.p, class_of, ctx->sm_count,
+                         ctx->stream));
+  ctx->launches += 1;
+  ctx->class_src = seq->data;
+  ctx->class_rows = seq->alloc_rows;
+  std::memcpy(ctx->class_lut, class_of, 32);
+  return LM_OK;
+}
+
 int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
   unsigned long long st[2] = {0, 0};
   LM_TRY(cudaMemcpyAsync(st, (uint8_t*)ctx->d_small.p + 272, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -455,7 +509,7 @@ void lm_ctx_destroy(lm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits})
+  for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits, &ctx->d_class})
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto& sl : ctx->slots) {
@@ -877,6 +931,7 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
                                               (new_alloc - seq->rows - seq->wrap) * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(nd); return fail(ctx, e, "grow sequence"); }
+    if (ctx->class_src == seq->data) ctx->class_src = nullptr;
     cudaFree(seq->data);
     seq->data = nd;
     seq->alloc_rows = new_alloc;
@@ -891,6 +946,7 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
   }
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   seq->wrap = wrap;
+  if (ctx->class_src == seq->data) ctx->class_src = nullptr;  // wrap rows changed
   return LM_OK;
 }
 
@@ -921,6 +977,7 @@ void lm_seq_free(lm_ctx* ctx, lm_seq* seq) {
   if (ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->class_src == seq->data) ctx->class_src = nullptr;  // the class-coded copy dies with its sequence
   }
   if (seq->owned && seq->data) cudaFree(seq->data);
   delete seq;
@@ -984,12 +1041,19 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
   const size_t n_rows = row_end - row_begin;
   PrunePlan plan;
-  if (ctx->opt_prune && seq->alphabet == LM_DNA && n_rows > 2 * ctx->opt_boot_rows) {
+  ProteinPlan pplan;
+  const bool protein = seq->alphabet == LM_PROTEIN;
+  if (ctx->opt_prune && n_rows > 2 * ctx->opt_boot_rows) {
     const double npos = (double)n_rows * 32.0;
-    plan = cached_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
+    if (protein) {
+      pplan = cached_protein_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
+      plan = pplan.plan;
+    } else {
+      plan = cached_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
+    }
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
-  if (plan.ok) LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
+  if (plan.ok) LM_CHECK(protein ? upload_table32(ctx, pssm, m, pssm_stride) : upload_table8(ctx, pssm, m, pssm_stride));
   const size_t off = (size_t)slot * 1024;
   uint8_t* small = (uint8_t*)ctx->d_small.p + off;
   LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
@@ -1001,6 +1065,13 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
                        row_begin + ctx->opt_boot_rows, nullptr, 0, 0.f, 0, nullptr, 0, false, off));
     PruneArgs pa;
     pa.seq = seq->data;
+    if (protein) {  // the filter reads class codes, the recheck the residues
+      LM_CHECK(ensure_class_copy(ctx, seq, pplan.class_of));
+      pa.seq = (const uint8_t*)ctx->d_class.p;
+      pa.seq_exact = seq->data;
+      pa.tab_stride = 32;
+      pa.pad_fill = pplan.class_of[20];
+    }
     pa.avail_rows = seq->alloc_rows;
     pa.row_begin = row_begin;
     pa.row_first = row_begin + ctx->opt_boot_rows;
@@ -1084,16 +1155,31 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
   LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
   PrunePlan plan;
-  if (ctx->opt_prune && seq->alphabet == LM_DNA && row_end - row_begin > 4096) {
-    plan = cached_plan(ctx, pssm, m, pssm_stride, false, (double)t, (double)(row_end - row_begin) * 32.0);
+  ProteinPlan pplan;
+  const bool protein = seq->alphabet == LM_PROTEIN;
+  if (ctx->opt_prune && row_end - row_begin > 4096) {
+    const double npos = (double)(row_end - row_begin) * 32.0;
+    if (protein) {
+      pplan = cached_protein_plan(ctx, pssm, m, pssm_stride, false, (double)t, npos);
+      plan = pplan.plan;
+    } else {
+      plan = cached_plan(ctx, pssm, m, pssm_stride, false, (double)t, npos);
+    }
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
   if (plan.ok) {
-    LM_CHECK(upload_table8(ctx, pssm, m, pssm_stride));
+    LM_CHECK(protein ? upload_table32(ctx, pssm, m, pssm_stride) : upload_table8(ctx, pssm, m, pssm_stride));
     uint8_t* small = (uint8_t*)ctx->d_small.p;
     LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
     PruneArgs pa;
     pa.seq = seq->data;
+    if (protein) {
+      LM_CHECK(ensure_class_copy(ctx, seq, pplan.class_of));
+      pa.seq = (const uint8_t*)ctx->d_class.p;
+      pa.seq_exact = seq->data;
+      pa.tab_stride = 32;
+      pa.pad_fill = pplan.class_of[20];
+    }
     pa.avail_rows = seq->alloc_rows;
     pa.row_begin = row_begin;
     pa.row_first = row_begin;
@@ -1397,6 +1483,29 @@ int lm_plan_filter(const float* pssm, size_t m, size_t pssm_stride, double thres
   out->eps = p.eps;
   out->est_pass_rate = p.est_pass_rate;
   out->est_cost = p.est_cost;
+  return p.r > 0 ? LM_OK : LM_EMPTY;
+}
+
+int lm_plan_filter_protein(const float* pssm, size_t m, size_t pssm_stride, double threshold, int is_argmax,
+                           double n_positions, int force_lookups, lm_filter_plan* out, uint8_t class_of[21]) {
+  if (!pssm || !out || !class_of || m == 0 || pssm_stride < 21) return LM_ERR_INVALID_ARG;
+  std::memset(out, 0, sizeof(*out));
+  const double t = is_argmax ? estimate_max_score_protein(pssm, m, pssm_stride, n_positions) : threshold;
+  const ProteinPlan pp = plan_prune_protein(pssm, m, pssm_stride, t, is_argmax != 0, n_positions, force_lookups);
+  const PrunePlan& p = pp.plan;
+  out->ok = p.ok ? 1 : 0;
+  out->r = p.r;
+  out->pair = 0;
+  out->pair_mul = p.pair_mul;
+  out->j0 = p.j0;
+  out->smax = p.smax;
+  for (int k = 0; k < 16; ++k) { out->tab_lo[k] = p.tab_lo[k]; out->tab_hi[k] = p.tab_hi[k]; }
+  out->c0 = p.c0;
+  out->delta = p.delta;
+  out->eps = p.eps;
+  out->est_pass_rate = p.est_pass_rate;
+  out->est_cost = p.est_cost;
+  for (int a = 0; a < 21; ++a) class_of[a] = pp.class_of[a];
   return p.r > 0 ? LM_OK : LM_EMPTY;
 }
 

@@ -33,6 +33,7 @@
 //   fp32score(p) >= T  ==>  sum_q(p) >= ceil((T - eps - c0) / delta)  (- 1 safety)
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "prune.cuh"
@@ -79,11 +80,11 @@ struct Ctl {
   uint64_t full[NSTAGE], empty[NSTAGE];
   struct { unsigned long long tile; uint32_t bias4; float thr; } desc[NSTAGE];
 };
-__host__ __device__ inline PSmem psmem(int m) {
+__host__ __device__ inline PSmem psmem(int m, int tab_stride) {
   PSmem s;
   uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);
   s.table_off = 0;
-  s.ctl_off = ((uint32_t)((m + 3) & ~3) * 8 * 4 + 127) & ~127u;
+  s.ctl_off = ((uint32_t)((m + 3) & ~3) * tab_stride * 4 + 127) & ~127u;
   s.queue_off = (s.ctl_off + (uint32_t)sizeof(Ctl) + 127) & ~127u;
   s.raw_off = s.queue_off + PW * QCAP * 4;
   s.raw_bytes = (tt * 32 + 127) & ~127u;
@@ -160,13 +161,25 @@ __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* t
   }
   return s;
 }
+// same from the residues in global memory (protein: the tile holds class codes); rows past the
+// readable extent are the default symbol
+__device__ __forceinline__ float exact_score_global(const PruneArgs& a, const float* tab, int m_pad, uint64_t row,
+                                                    uint32_t col) {
+  float s = 0.0f;
+  for (int j = 0; j < m_pad; ++j) {
+    const uint64_t r = row + j;
+    const uint32_t sym = r < a.avail_rows ? a.seq_exact[r * 32 + col] : a.pad_sym;
+    s = __fadd_rn(s, tab[j * a.tab_stride + sym]);
+  }
+  return s;
+}
 
 template <int R, bool PAIR, bool THR>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.plan.m;
-  const PSmem S = psmem(m);
+  const PSmem S = psmem(m, a.tab_stride);
   const uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);  // rows staged per tile (tile + halo)
   float* tab = reinterpret_cast<float*>(smem + S.table_off);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + S.ctl_off);
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     mbar_fence_init();
   }
   const int m_pad = (m + 3) & ~3;
-  for (int i = tid; i < m_pad * 8; i += PT) tab[i] = a.table[i];  // [m_pad][8], rows >= m are +0.0
+  for (int i = tid; i < m_pad * a.tab_stride; i += PT) tab[i] = a.table[i];  // rows >= m are +0.0
   __syncthreads();  // the only CTA-wide barrier: from here on warps meet through mbarriers only
 
   if (warp == PW) {
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       const uint32_t wend = wrow0 + WARP_ROWS + ((m + 3) & ~3);
       if (avail < wend) {
         uint32_t w0 = (avail > wrow0 ? (uint32_t)avail : wrow0) * 8, w1 = wend * 8;
-        uint32_t fill = a.pad_sym * 0x01010101u;
+        uint32_t fill = a.pad_fill * 0x01010101u;
         for (uint32_t w = w0 + lane; w < w1; w += 32) reinterpret_cast<uint32_t*>(rawb)[w] = fill;
         __syncwarp();
       }
@@ -416,14 +429,16 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
             if (!((code >> b) & 1u)) continue;
             const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
             if (row >= tile_valid) continue;
-            float sc = exact_score(rawb, tab, m_pad, row, col);
+            float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
+                                   : exact_score(rawb, tab, m_pad, row, col);
             if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
           }
           n_cand += nq;
         } else {
           for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
             uint32_t row = wrow0 + (p >> 5), col = p & 31;
-            float sc = exact_score(rawb, tab, m_pad, row, col);
+            float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
+                                   : exact_score(rawb, tab, m_pad, row, col);
             if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
           }
           n_over += 1;
@@ -443,7 +458,7 @@ template <bool THR>
 cudaError_t launch_r(const PruneArgs& a, int sm_count, cudaStream_t stream) {
   if (a.row_end <= a.row_first) return cudaSuccess;
   const uint64_t num_tiles = (a.row_end - a.row_first + PTILE_ROWS - 1) / PTILE_ROWS;
-  const PSmem S = psmem(a.plan.m);
+  const PSmem S = psmem(a.plan.m, a.tab_stride);
   void (*kern)(const PruneArgs, uint64_t) = nullptr;
   if (a.plan.pair) {
     switch (a.plan.r) {
@@ -578,7 +593,81 @@ double filter_cost(int r, int w, bool pair, double pass) {
   // the candidate paths are partly hidden behind the other warps' filter work
   return core + 0.4 * push + 0.6 * recheck + overflow;
 }
-constexpr double EXACT_COST = 350.0;  // exact-everywhere kernel, same unit
+constexpr double EXACT_COST = 350.0;  // exact-everywhere kernel (width-20 DNA), same unit
+
+// Quantise R look-up units into byte tables: clamp every unit from below at (its maximum - clamp),
+// pick the common step delta so that the largest attainable sum is <= 127, round every entry UP.
+// Returns false when no valid tables exist.  On success `pass` is the probability that a random
+// window reaches the planning threshold t_plan, by exact convolution of the units' distributions.
+struct Quantised {
+  int q[16][8];
+  int smax = 0;
+  double c0 = 0, delta = 1, pass = 1;
+};
+bool quantise_units(Unit* u, int R, double clamp, double restmax, double t_plan, double eps, Quantised& out) {
+  double base[16], range_sum = 0, base_sum = 0;
+  for (int k = 0; k < R; ++k) {
+    double mx = -INFINITY, mn = INFINITY;
+    for (int e = 0; e < u[k].n; ++e) mx = std::max(mx, u[k].v[e]);
+    if (!std::isfinite(mx)) return false;
+    for (int e = 0; e < u[k].n; ++e) {
+      u[k].v[e] = std::max(u[k].v[e], mx - clamp);
+      mn = std::min(mn, u[k].v[e]);
+    }
+    base[k] = mn;
+    base_sum += mn;
+    range_sum += mx - mn;
+  }
+  if (!(range_sum > 0)) return false;
+  const double delta = range_sum / (127.0 - R);
+  int smax = 0;
+  for (int k = 0; k < R; ++k) {
+    int mxq = 0;
+    for (int e = 0; e < u[k].n; ++e) {
+      int v = (int)std::ceil((u[k].v[e] - base[k]) / delta - 1e-9);
+      if (v < 0) v = 0;
+      while (base[k] + v * delta < u[k].v[e]) v++;  // the bound must hold despite the slack
+      out.q[k][e] = v;
+      mxq = std::max(mxq, v);
+    }
+    for (int e = u[k].n; e < 8; ++e) out.q[k][e] = 0;
+    smax += mxq;
+  }
+  if (smax > 127) return false;
+  out.smax = smax;
+  out.delta = delta;
+  out.c0 = base_sum + restmax;
+  const double need = (t_plan - eps - out.c0) / delta;
+  const int qthr = need > 1.0 ? (int)std::ceil(need) - 1 : 0;
+  if (qthr <= 0) out.pass = 1.0;
+  else if (qthr > smax) out.pass = 0.0;
+  else {
+    double d[128] = {0}, nd[128];
+    d[0] = 1.0;
+    for (int k = 0; k < R; ++k) {
+      std::fill(nd, nd + 128, 0.0);
+      for (int e = 0; e < u[k].n; ++e)
+        if (u[k].prob[e] > 0)
+          for (int i = 0; i + out.q[k][e] < 128; ++i) nd[i + out.q[k][e]] += u[k].prob[e] * d[i];
+      std::copy(nd, nd + 128, d);
+    }
+    out.pass = 0;
+    for (int i = qthr; i < 128; ++i) out.pass += d[i];
+  }
+  return true;
+}
+
+void store_tables(PrunePlan& plan, const Quantised& Q, int R) {
+  for (int k = 0; k < 16; ++k) plan.tab_lo[k] = plan.tab_hi[k] = 0;
+  for (int k = 0; k < R; ++k) {
+    plan.tab_lo[k] = (uint32_t)Q.q[k][0] | ((uint32_t)Q.q[k][1] << 8) | ((uint32_t)Q.q[k][2] << 16) | ((uint32_t)Q.q[k][3] << 24);
+    plan.tab_hi[k] = (uint32_t)Q.q[k][4] | ((uint32_t)Q.q[k][5] << 8) | ((uint32_t)Q.q[k][6] << 16) | ((uint32_t)Q.q[k][7] << 24);
+  }
+  plan.smax = Q.smax;
+  plan.c0 = Q.c0;
+  plan.delta = Q.delta;
+  plan.est_pass_rate = Q.pass;
+}
 
 }  // namespace
 
@@ -637,56 +726,9 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
         U.v[4] = std::max(U.v[4], r.w[rf * 5 + 4] + hall);
       }
     }
-    // clamp from below, per-unit base, quantisation step
-    double base[16], range_sum = 0, base_sum = 0;
-    for (int k = 0; k < R; ++k) {
-      double mx = -INFINITY, mn = INFINITY;
-      for (int e = 0; e < u[k].n; ++e) mx = std::max(mx, u[k].v[e]);
-      if (!std::isfinite(mx)) return;
-      for (int e = 0; e < u[k].n; ++e) {
-        u[k].v[e] = std::max(u[k].v[e], mx - C * (pair ? 1.5 : 1.0));
-        mn = std::min(mn, u[k].v[e]);
-      }
-      base[k] = mn;
-      base_sum += mn;
-      range_sum += mx - mn;
-    }
-    if (!(range_sum > 0)) return;
-    const double delta = range_sum / (127.0 - R);
-    int q[16][8], smax = 0;
-    for (int k = 0; k < R; ++k) {
-      int mxq = 0;
-      for (int e = 0; e < u[k].n; ++e) {
-        q[k][e] = (int)std::ceil((u[k].v[e] - base[k]) / delta - 1e-9);
-        if (q[k][e] < 0) q[k][e] = 0;
-        while (base[k] + q[k][e] * delta < u[k].v[e]) q[k][e]++;  // the bound must hold despite the slack
-        mxq = std::max(mxq, q[k][e]);
-      }
-      for (int e = u[k].n; e < 8; ++e) q[k][e] = 0;
-      smax += mxq;
-    }
-    if (smax > 127) return;
-    const double c0 = base_sum + restmax;
-    // pass rate under uniform ACGT at t_plan
-    double need = (t_plan - eps - c0) / delta;
-    int qthr = need > 1.0 ? (int)std::ceil(need) - 1 : 0;
-    double pass;
-    if (qthr <= 0) pass = 1.0;
-    else if (qthr > smax) pass = 0.0;
-    else {
-      double d[128] = {0}, nd[128];
-      d[0] = 1.0;
-      for (int k = 0; k < R; ++k) {
-        std::fill(nd, nd + 128, 0.0);
-        for (int e = 0; e < u[k].n; ++e)
-          if (u[k].prob[e] > 0)
-            for (int i = 0; i + q[k][e] < 128; ++i) nd[i + q[k][e]] += u[k].prob[e] * d[i];
-        std::copy(nd, nd + 128, d);
-      }
-      pass = 0;
-      for (int i = qthr; i < 128; ++i) pass += d[i];
-    }
-    const double cost = filter_cost(R, std::min<int>(W, (int)m - j0), pair, pass);
+    Quantised Q;
+    if (!quantise_units(u, R, C * (pair ? 1.5 : 1.0), restmax, t_plan, eps, Q)) return;
+    const double cost = filter_cost(R, std::min<int>(W, (int)m - j0), pair, Q.pass);
     if (cost < best_cost) {
       best_cost = cost;
       best.m = (int)m;
@@ -694,19 +736,9 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
       best.pair = pair ? 1 : 0;
       best.pair_mul = mul;
       best.j0 = j0;
-      best.smax = smax;
-      best.c0 = c0;
-      best.delta = delta;
       best.eps = eps;
-      best.est_pass_rate = pass;
       best.est_cost = cost;
-      for (int k = 0; k < 16; ++k) best.tab_lo[k] = best.tab_hi[k] = 0;
-      for (int k = 0; k < R; ++k) {
-        best.tab_lo[k] = (uint32_t)q[k][0] | ((uint32_t)q[k][1] << 8) | ((uint32_t)q[k][2] << 16) |
-                         ((uint32_t)q[k][3] << 24);
-        best.tab_hi[k] = (uint32_t)q[k][4] | ((uint32_t)q[k][5] << 8) | ((uint32_t)q[k][6] << 16) |
-                         ((uint32_t)q[k][7] << 24);
-      }
+      store_tables(best, Q, R);
     }
   };
 
@@ -759,6 +791,179 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
     }
   }
   best.ok = best_cost < EXACT_COST && best.r > 0;
+  return best;
+}
+
+// ------------------------------------------------------------------ protein
+
+namespace {
+constexpr int PK = 21, PX = 20;  // protein alphabet size, code of the default symbol X
+
+bool load_rows_protein(const float* pssm, size_t m, size_t stride, std::vector<double>& w, std::vector<double>& rowmax) {
+  w.resize(m * PK);
+  rowmax.resize(m);
+  for (size_t j = 0; j < m; ++j) {
+    double mx = -INFINITY;
+    for (int a = 0; a < PK; ++a) {
+      const float x = pssm[j * stride + a];
+      if (std::isnan(x) || x == INFINITY) return false;
+      w[j * PK + a] = x;
+      if (x > mx) mx = x;
+    }
+    if (!std::isfinite(mx)) return false;
+    rowmax[j] = mx;
+  }
+  return true;
+}
+}  // namespace
+
+double estimate_max_score_protein(const float* pssm, size_t m, size_t stride, double n_positions) {
+  std::vector<double> w, rowmax;
+  if (!load_rows_protein(pssm, m, stride, w, rowmax)) return -INFINITY;
+  // distribution of the score under a uniform 20-letter background on a 1/16 grid
+  const double res = 1.0 / 16.0, floor_ = 24.0;
+  std::vector<int> qw(m * PX);
+  int span = 0;
+  double maxsum = 0;
+  for (size_t j = 0; j < m; ++j) {
+    double mx = -INFINITY;
+    for (int a = 0; a < PX; ++a) mx = std::max(mx, w[j * PK + a]);
+    if (!std::isfinite(mx)) return -INFINITY;
+    maxsum += mx;
+    int mn = 0;
+    for (int a = 0; a < PX; ++a) {
+      qw[j * PX + a] = (int)std::floor((std::max(w[j * PK + a], mx - floor_) - mx) / res);
+      mn = std::min(mn, qw[j * PX + a]);
+    }
+    span += -mn;
+  }
+  std::vector<double> d(span + 1, 0.0), nd(span + 1);
+  d[0] = 1.0;
+  for (size_t j = 0; j < m; ++j) {
+    std::fill(nd.begin(), nd.end(), 0.0);
+    for (int a = 0; a < PX; ++a) {
+      const int sft = -qw[j * PX + a];
+      for (int i = 0; i + sft <= span; ++i) nd[i + sft] += d[i] / PX;
+    }
+    d.swap(nd);
+  }
+  double cum = 0;
+  for (int i = 0; i <= span; ++i) {
+    cum += d[i];
+    if (cum * n_positions >= 1.0) return maxsum - (i + 1) * res;
+  }
+  return maxsum - span * res;
+}
+
+ProteinPlan plan_prune_protein(const float* pssm, size_t m, size_t stride, double t_plan, bool t_is_estimate,
+                               double n_positions, int force_r) {
+  ProteinPlan best;
+  std::memset(best.class_of, 0, sizeof(best.class_of));
+  std::vector<double> w, rowmax;
+  if (m < 4 || m > 64 || !load_rows_protein(pssm, m, stride, w, rowmax)) return best;
+  (void)n_positions;
+  if (t_is_estimate) t_plan -= 1.0;
+  double abs_sum = 0, max_total = 0;
+  for (size_t j = 0; j < m; ++j) {
+    double am = 0;
+    for (int a = 0; a < PK; ++a)
+      if (std::isfinite(w[j * PK + a])) am = std::max(am, std::fabs(w[j * PK + a]));
+    abs_sum += am;
+    max_total += rowmax[j];
+  }
+  const double eps = 2.0 * (double)m * std::ldexp(1.0, -24) * abs_sum + 1e-30;
+  std::vector<double> info(m);
+  for (size_t j = 0; j < m; ++j) {
+    double e = 0;
+    for (int a = 0; a < PX; ++a) e += std::min(8.0, rowmax[j] - std::max(w[j * PK + a], rowmax[j] - 8.0)) / PX;
+    info[j] = e;
+  }
+  static const int RS[] = {4, 6, 8, 10, 12, 16};
+  static const double CS3[] = {6.0, 12.0, CLAMP_FLOOR};
+  // the class-map pass moves 2 bytes per residue through HBM: ~43 issue-slot equivalents per 128 positions
+  const double PREPASS_COST = 43.0;
+  const double exact_cost = 17.5 * (double)((m + 3) & ~(size_t)3);  // exact kernel: ~17.5 per motif row
+  double best_cost = 1e300;
+  for (int R : RS) {
+    if (R > (int)m || (force_r && R != force_r)) continue;
+    // the three most informative windows of R rows
+    int win[3] = {-1, -1, -1};
+    double sc[3] = {-1, -1, -1};
+    for (int j0 = 0; j0 + R <= (int)m; ++j0) {
+      double v = 0;
+      for (int k = 0; k < R; ++k) v += info[j0 + k];
+      for (int q = 0; q < 3; ++q)
+        if (v > sc[q]) {
+          for (int z = 2; z > q; --z) { sc[z] = sc[z - 1]; win[z] = win[z - 1]; }
+          sc[q] = v; win[q] = j0;
+          break;
+        }
+    }
+    for (int j0 : win) {
+      if (j0 < 0) continue;
+      // cluster the 21 residues into 8 classes on the window's (clamped) columns: greedy merging of
+      // the pair of classes whose union adds the least over-estimate, weighted by class size
+      std::vector<std::vector<int>> cls(PK);
+      for (int a = 0; a < PK; ++a) cls[a] = {a};
+      auto wc = [&](int k, int a) { return std::max(w[(j0 + k) * PK + a], rowmax[j0 + k] - 12.0); };
+      auto cmax = [&](const std::vector<int>& c, int k) {
+        double mx = -INFINITY;
+        for (int a : c) mx = std::max(mx, wc(k, a));
+        return mx;
+      };
+      auto weight = [&](const std::vector<int>& c) {
+        int n = 0;
+        for (int a : c) n += a != PX;
+        return (double)n;
+      };
+      while (cls.size() > 8) {
+        double bestc = INFINITY;
+        size_t bi = 0, bj = 1;
+        for (size_t i = 0; i < cls.size(); ++i)
+          for (size_t j = i + 1; j < cls.size(); ++j) {
+            double cost = 0;
+            for (int k = 0; k < R; ++k) {
+              const double mi = cmax(cls[i], k), mj = cmax(cls[j], k), mu = std::max(mi, mj);
+              cost += weight(cls[i]) * (mu - mi) + weight(cls[j]) * (mu - mj);
+            }
+            if (cost < bestc) { bestc = cost; bi = i; bj = j; }
+          }
+        cls[bi].insert(cls[bi].end(), cls[bj].begin(), cls[bj].end());
+        cls.erase(cls.begin() + bj);
+      }
+      double restmax = max_total;
+      for (int k = 0; k < R; ++k) restmax -= rowmax[j0 + k];
+      for (double C : CS3) {
+        Unit u[16];
+        for (int k = 0; k < R; ++k) {
+          u[k].n = (int)cls.size();
+          for (size_t e = 0; e < cls.size(); ++e) {
+            double mx = -INFINITY;
+            for (int a : cls[e]) mx = std::max(mx, w[(j0 + k) * PK + a]);  // true weights: the bound must hold
+            u[k].v[e] = mx;
+            u[k].prob[e] = weight(cls[e]) / PX;
+          }
+        }
+        Quantised Q;
+        if (!quantise_units(u, R, C, restmax, t_plan, eps, Q)) continue;
+        const double cost = filter_cost(R, R, false, Q.pass) + PREPASS_COST;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best.plan.m = (int)m;
+          best.plan.r = R;
+          best.plan.pair = 0;
+          best.plan.pair_mul = 2;
+          best.plan.j0 = j0;
+          best.plan.eps = eps;
+          best.plan.est_cost = cost;
+          store_tables(best.plan, Q, R);
+          for (size_t e = 0; e < cls.size(); ++e)
+            for (int a : cls[e]) best.class_of[a] = (uint8_t)e;
+        }
+      }
+    }
+  }
+  best.plan.ok = best.plan.r > 0 && best_cost < exact_cost;
   return best;
 }
 

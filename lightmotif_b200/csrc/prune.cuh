@@ -48,15 +48,30 @@ PrunePlan plan_prune(const float* pssm, size_t m, size_t stride, double t_plan, 
 // expected number of cells with score >= t among n uniform-random positions is ~1.
 double estimate_max_score(const float* pssm, size_t m, size_t stride, double n_positions);
 
+// Protein: the 21-letter alphabet does not fit a PRMT table, so the filter runs on a CLASS-CODED copy
+// of the sequence: the residues are partitioned into 8 classes (chosen per matrix by clustering its
+// columns), a look-up entry is the best weight within the class -- still an upper bound.
+struct ProteinPlan {
+  PrunePlan plan;        // single-row look-ups over class codes 0..7 (tab_lo = classes 0..3, tab_hi = 4..7)
+  uint8_t class_of[32];  // residue code (0..20) -> class
+};
+ProteinPlan plan_prune_protein(const float* pssm, size_t m, size_t stride, double t_plan, bool t_is_estimate,
+                               double n_positions, int force_r = 0);
+double estimate_max_score_protein(const float* pssm, size_t m, size_t stride, double n_positions);
+
 struct PruneArgs {
-  const uint8_t* seq = nullptr;  // [avail_rows][32]
+  const uint8_t* seq = nullptr;  // [avail_rows][32]: what the FILTER reads (DNA symbols / protein class codes)
+  // protein: the residues themselves, same shape, for the exact recheck (nullptr: recheck from the tile)
+  const uint8_t* seq_exact = nullptr;
+  int tab_stride = 8;            // floats per row of `table` (8 DNA, 32 protein)
   uint64_t avail_rows = 0;
   uint64_t row_begin = 0;        // first row of the scored range (positions are relative to it)
   uint64_t row_first = 0;        // first row THIS launch scans (>= row_begin; rows before were bootstrapped)
   uint64_t row_end = 0;
-  uint8_t pad_sym = 4;
+  uint8_t pad_sym = 4;           // default symbol of the alphabet (exact recheck past the readable extent)
+  uint8_t pad_fill = 4;          // what the FILTER sees past the readable extent (DNA: N; protein: class of X)
   uint32_t one = 1;              // opaque multiplier: `acc = p * one + acc` keeps the byte-lane adds on the FMA pipe (IMAD)
-  const float* table = nullptr;  // device: [m rounded up to 4][8] f32 (A,C,T,G,N,0,0,0), pad rows +0.0
+  const float* table = nullptr;  // device: [m rounded up to 4][tab_stride] f32, pad rows +0.0
   PrunePlan plan;
   // argmax mode: colkeys[32] holds the running per-column winners (read for the
   // dynamic threshold, updated with atomicMax)

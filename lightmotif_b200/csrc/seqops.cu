@@ -216,6 +216,29 @@ __global__ void __launch_bounds__(ST_THREADS, LM_ST_MINB) stripe_kernel(const ui
   if (FROM_ASCII && bad != ~0ull) atomicMin(first_bad, bad);
 }
 
+// Residue -> class code (protein filter, prune.cuh): dst[i] = lut[src[i]], 16 bytes per thread.
+// HBM-bound 1 + 1 bytes per residue.
+struct ClassLut { uint8_t v[32]; };
+__global__ void __launch_bounds__(ENC_THREADS) classmap_kernel(const uint4* __restrict__ src, uint64_t nvec,
+                                                                uint4* __restrict__ dst, const ClassLut lut) {
+  __shared__ uint8_t sl[32];
+  if (threadIdx.x < 32) sl[threadIdx.x] = lut.v[threadIdx.x];
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const uint4 x = src[v];
+    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) o |= (uint32_t)sl[(w[q] >> (8 * b)) & 31] << (8 * b);
+      w[q] = o;
+    }
+    dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // configure_wrap on an existing device matrix: rows [rows + old_wrap, rows + new_wrap)
 // cell (r, c) = base cell (r % rows, c + r / rows), default symbol past column 31.
 __global__ void wrap_kernel(uint8_t* data, uint64_t rows, uint64_t r_begin, uint64_t r_end, uint8_t pad) {
@@ -291,6 +314,17 @@ cudaError_t launch_stripe(const uint8_t* src, bool from_ascii, uint64_t n, uint6
     stripe_kernel<true><<<grid, ST_THREADS, 0, stream>>>(src, n, rows, row0, out_rows, dst, alphabet, pad, first_bad);
   else
     stripe_kernel<false><<<grid, ST_THREADS, 0, stream>>>(src, n, rows, row0, out_rows, dst, alphabet, pad, first_bad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_classmap(const uint8_t* src, uint64_t n_bytes, uint8_t* dst, const uint8_t* lut32, int sm_count,
+                            cudaStream_t stream) {
+  if (n_bytes == 0) return cudaSuccess;
+  ClassLut lut;
+  for (int i = 0; i < 32; ++i) lut.v[i] = lut32[i];
+  const uint64_t nvec = n_bytes / 16;  // striped matrices are multiples of 32 bytes
+  classmap_kernel<<<grid_for(nvec, ENC_THREADS, sm_count, 16), ENC_THREADS, 0, stream>>>(
+      reinterpret_cast<const uint4*>(src), nvec, reinterpret_cast<uint4*>(dst), lut);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,9 @@ cudaError_t launch_stripe(const uint8_t* src, bool from_ascii, uint64_t n, uint6
 // Fill striped rows [r_begin, r_end) (>= rows) from the base rows.
 cudaError_t launch_wrap(uint8_t* data, uint64_t rows, uint64_t r_begin, uint64_t r_end, int alphabet,
                         cudaStream_t stream);
+// dst[i] = lut32[src[i] & 31] over n_bytes (a multiple of 16) bytes: residue -> class code.
+cudaError_t launch_classmap(const uint8_t* src, uint64_t n_bytes, uint8_t* dst, const uint8_t* lut32, int sm_count,
+                            cudaStream_t stream);
 cudaError_t launch_synth(uint8_t* dst, uint64_t out_rows, uint64_t rows, uint64_t row0,
                          uint64_t total_length, uint64_t seed, int alphabet, int sm_count,
                          cudaStream_t stream);

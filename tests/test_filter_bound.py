@@ -108,3 +108,50 @@ def test_planner_prefers_the_filter_for_informative_motifs():
     flat[:, 4] = -np.inf
     p2 = lm.plan_filter(flat, n_positions=5e9)
     assert p2 is None or not p2["ok"]
+
+
+@pytest.mark.parametrize("m,kind", [(15, "acp"), (23, "acp"), (8, "random"), (12, "neginf"), (16, "finite_x")])
+def test_protein_bound_dominates_score(m, kind):
+    """Same property for the protein flavour: 8 residue classes, entry = best weight in the class."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"prot-{m}-{kind}".encode()))
+    if kind == "acp":
+        pats = ["SFKELGFDSLTAVELRNRLAAAT", "AFKELGFDSLAAIQLRNRLLADV", "PSRRLGFDSLTAVELRNQLAAST",
+                "AFREIGFDSLTAVELRNRLGAAA", "SLMEEGLDSLAAVELGGTLQRDT", "GFFDLGMDSLMAVELRRRIEQGV"]
+        pssm = O.pssm_from_sequences(O.PROTEIN, pats, 0.1)[:m]
+    elif kind == "finite_x":
+        pssm = rng.normal(0, 2, size=(m, 21)).astype(np.float32)
+    else:
+        counts = rng.integers(0, 6 if kind == "random" else 2, size=(m, 21)).astype(np.uint32)
+        counts[:, 20] = 0
+        counts[np.arange(m), rng.integers(0, 20, m)] += 40
+        pssm = O.pssm_from_counts(O.PROTEIN, counts, 0.1 if kind == "random" else 0.0)
+    checked = 0
+    for lookups in (0, 4, 6, 8, 10, 12, 16):
+        for thr in (None, 5.0):
+            plan = lm.plan_filter_protein(pssm, threshold=thr, lookups=lookups)
+            if plan is None:
+                continue
+            cls = plan["class_of"]
+            assert cls.max() <= 7 and 0 < plan["smax"] <= 127
+            n = 4000
+            win = rng.integers(0, 20, size=(n, m)).astype(np.uint8)
+            win[: n // 8][rng.random((n // 8, m)) < 0.1] = 20                 # X
+            win[n // 8: n // 4] = np.argmax(pssm[:, :20], axis=1)[None, :]     # consensus with mismatches
+            flip = rng.random((n // 8, m)) < 0.1
+            win[n // 8: n // 4][flip] = rng.integers(0, 20, size=int(flip.sum()))
+            real = pssm.astype(np.float64)[np.arange(m)[None, :], win].sum(axis=1)
+            s32 = np.zeros(n, dtype=np.float32)
+            for j in range(m):
+                s32 = (s32 + pssm[j, win[:, j]]).astype(np.float32)
+            sq = np.zeros(n, dtype=np.int64)
+            for k in range(plan["r"]):
+                tab = np.array([(plan["tab_lo"][k] >> (8 * b)) & 0xFF for b in range(4)] +
+                               [(plan["tab_hi"][k] >> (8 * b)) & 0xFF for b in range(4)], dtype=np.int64)
+                sq += tab[cls[win[:, plan["j0"] + k]]]
+            assert np.all(plan["c0"] + plan["delta"] * sq >= real - 1e-9)
+            finite = np.isfinite(s32)
+            need = np.ceil((s32[finite].astype(np.float64) - plan["eps"] - plan["c0"]) / plan["delta"]) - 1
+            assert np.all(sq[finite] >= need)
+            checked += 1
+    assert checked >= 2

@@ -162,3 +162,77 @@ def test_all_equal_sequence_ties(dna):
             got = seq.score_argmax(pssm, rule=r)
             rr, cc = O.argmax(ref, r)
             assert (got["row"], got["col"]) == (rr, cc), (fmode, r)
+
+
+# ------------------------------------------------------------------ protein
+@pytest.fixture()
+def prot(lm):
+    p = lm.Pipeline.cuda(lm.PROTEIN)
+    yield p
+    p.close()
+
+
+def protein_pssm(rng, m, kind):
+    if kind == "acp":  # the reference's bench motif (lightmotif/benches/score.rs:179-186)
+        pats = ["SFKELGFDSLTAVELRNRLAAAT", "AFKELGFDSLAAIQLRNRLLADV", "PSRRLGFDSLTAVELRNQLAAST",
+                "AFREIGFDSLTAVELRNRLGAAA", "SLMEEGLDSLAAVELGGTLQRDT", "GFFDLGMDSLMAVELRRRIEQGV"]
+        return O.pssm_from_sequences(O.PROTEIN, pats, 0.1)[:m]
+    if kind == "random":
+        counts = rng.integers(0, 6, size=(m, 21)).astype(np.uint32)
+        counts[:, 20] = 0
+        counts[np.arange(m), rng.integers(0, 20, m)] += 60
+        return O.pssm_from_counts(O.PROTEIN, counts, 0.1)
+    if kind == "neginf":
+        counts = rng.integers(0, 2, size=(m, 21)).astype(np.uint32)
+        counts[:, 20] = 0
+        counts[np.arange(m), rng.integers(0, 20, m)] += 25
+        return O.pssm_from_counts(O.PROTEIN, counts, 0.0)
+    if kind == "finite_x":
+        return rng.normal(0, 2, size=(m, 21)).astype(np.float32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("m,kind", [(15, "acp"), (23, "acp"), (8, "random"), (12, "neginf"), (16, "finite_x"), (30, "random")])
+def test_protein_filter_equals_exact(prot, m, kind):
+    """Protein fused scans through the class-coded filter (8 residue classes, exact recheck from the
+    residues) == scoring every cell: same cell, bit-identical score, same hit list."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(f"prot-{m}-{kind}".encode()))
+    n = 1_200_007
+    pssm = protein_pssm(rng, m, kind)
+    sym = O.synth_protein(n)
+    sym[::997] = 20                      # X
+    sym[5000:5600] = 3                   # low complexity
+    # plant near-consensus windows so that thresholds have hits
+    cons = np.argmax(pssm[:, :20], axis=1).astype(np.uint8)
+    for at in (1234, 400_000, n - m - 3):
+        sym[at:at + m] = cons
+        sym[at + 2] = (cons[2] + 1) % 20
+    seq = prot.sequence_from_symbols(sym, m - 1)
+    prot.set_boot_rows(2048)
+    prot.set_prune(0)
+    ref = seq.score(pssm)
+    want = O.score_f32(pssm, O.stripe(O.PROTEIN, sym, 32, m - 1), n)
+    assert np.array_equal(ref.view(np.uint32), want.view(np.uint32))
+    finite = ref[np.isfinite(ref)]
+    ts = [float(np.quantile(finite, q)) for q in (0.999999, 0.9999, 0.5)]
+    exact = {"argmax": {r: seq.score_argmax(pssm, rule=r) for r in (0, 1, 2)},
+             "thr": {t: seq.score_threshold(pssm, t) for t in ts}}
+    assert not prot.last_stats["pruned"]
+    prot.set_prune(2)
+    for r in (0, 1, 2):
+        got = seq.score_argmax(pssm, rule=r)
+        assert prot.last_stats["pruned"]
+        assert got == exact["argmax"][r], (r, got, exact["argmax"][r])
+        rr, cc = O.argmax(want, r)
+        assert (got["row"], got["col"]) == (rr, cc)
+    for t in ts:
+        assert seq.score_threshold(pssm, t) == exact["thr"][t], t
+    # a second sequence at (possibly) the same address must not see the first one's class copy
+    seq.free()
+    sym2 = O.synth_protein(n, offset=12345)
+    seq2 = prot.sequence_from_symbols(sym2, m - 1)
+    prot.set_prune(0)
+    e2 = seq2.score_argmax(pssm)
+    prot.set_prune(2)
+    assert seq2.score_argmax(pssm) == e2
