@@ -131,6 +131,10 @@ float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
 /* filter look-up flavour: 0 = planner decides, 1 = one motif row per look-up,
  * 2 = paired (one row exactly + one class bit of the next row per look-up) */
 #define LM_OPT_FILTER_MODE 5
+/* protein filter: 1 (default) = keep the class-coded copy of the last scanned
+ * sequence and reuse it while sequence and class map are unchanged, 0 = rebuild
+ * it on every call */
+#define LM_OPT_CLASS_CACHE 6
 int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
 /* statistics of the most recent fused call: out[0] = cells rechecked exactly,
  * out[1] = tiles that fell back to exact scoring, out[2] = 1 if the filter

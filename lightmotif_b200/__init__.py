@@ -367,6 +367,10 @@ class Pipeline:
         """LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single-row look-ups, 2 = paired look-ups."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 5, int(mode)))
 
+    def set_class_cache(self, on):
+        """LM_OPT_CLASS_CACHE: reuse (1) or rebuild (0) the class-coded copy of a protein sequence."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 6, int(on)))
+
     def set_reserve_sms(self, n):
         """LM_OPT_RESERVE_SMS: SMs left free for concurrent kernels (NCCL)."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 4, int(n)))

@@ -47,6 +47,7 @@ struct lm_ctx {
   int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
   int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
   int opt_filter_mode = 0;                // LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single rows, 2 = paired rows
+  int opt_class_cache = 1;                // LM_OPT_CLASS_CACHE: reuse the class-coded copy of a protein sequence
   int opt_reserve_sms = 0;                // LM_OPT_RESERVE_SMS: SMs left free for concurrent (NCCL) kernels
   size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
   uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
@@ -378,7 +379,7 @@ int upload_table32(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
 }
 
 int ensure_class_copy(lm_ctx* ctx, const lm_seq* seq, const uint8_t* class_of) {
-  if (seq->owned && ctx->class_src == seq->data && ctx->class_rows == seq->alloc_rows && ctx->d_class.p &&
+  if (ctx->opt_class_cache && seq->owned && ctx->class_src == seq->data && ctx->class_rows == seq->alloc_rows && ctx->d_class.p &&
       std::memcmp(ctx->class_lut, class_of, 32) == 0)
     return LM_OK;  // same (library-owned, hence unmodified) sequence, same classes: the copy is still valid
   LM_CHECK(ensure(ctx, ctx->d_class, seq->alloc_rows * 32));
@@ -550,6 +551,10 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
   }
   if (option == LM_OPT_FILTER_MODE && value >= 0 && value <= 2) {
     ctx->opt_filter_mode = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_CLASS_CACHE && (value == 0 || value == 1)) {
+    ctx->opt_class_cache = value;
     return LM_OK;
   }
   if (option == LM_OPT_BOOT_ROWS && value >= 1) {

@@ -225,17 +225,25 @@ __global__ void __launch_bounds__(ENC_THREADS) classmap_kernel(const uint4* __re
   if (threadIdx.x < 32) sl[threadIdx.x] = lut.v[threadIdx.x];
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const uint4 x = src[v];
-    uint32_t w[4] = {x.x, x.y, x.z, x.w};
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += U * stride) {
+    uint4 x[U];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t o = 0;
+    for (int u = 0; u < U; ++u)
+      if (v0 + u * stride < nvec) x[u] = __ldg(&src[v0 + u * stride]);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) o |= (uint32_t)sl[(w[q] >> (8 * b)) & 31] << (8 * b);
-      w[q] = o;
+    for (int u = 0; u < U; ++u) {
+      if (v0 + u * stride >= nvec) break;
+      uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o |= (uint32_t)sl[(w[q] >> (8 * b)) & 31] << (8 * b);
+        w[q] = o;
+      }
+      dst[v0 + u * stride] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    dst[v] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -323,7 +331,7 @@ cudaError_t launch_classmap(const uint8_t* src, uint64_t n_bytes, uint8_t* dst, 
   ClassLut lut;
   for (int i = 0; i < 32; ++i) lut.v[i] = lut32[i];
   const uint64_t nvec = n_bytes / 16;  // striped matrices are multiples of 32 bytes
-  classmap_kernel<<<grid_for(nvec, ENC_THREADS, sm_count, 16), ENC_THREADS, 0, stream>>>(
+  classmap_kernel<<<grid_for((nvec + 3) / 4, ENC_THREADS, sm_count, 8), ENC_THREADS, 0, stream>>>(
       reinterpret_cast<const uint4*>(src), nvec, reinterpret_cast<uint4*>(dst), lut);
   return cudaGetLastError();
 }

@@ -112,11 +112,13 @@ def main():
                                       "classes chosen per matrix, class-coded copy of the sequence (one extra pass, cached "
                                       "per sequence + matrix), PRMT filter on the class codes, exact recheck from the residues"}
     prot.set_prune(1)
-    r1 = seq.score_argmax(pp)
-    first_ms = prot.last_kernel_ms          # includes the class-map pass
+    r1 = seq.score_argmax(pp)               # allocates the class-copy buffer
+    prot.set_class_cache(0)
+    first_ms, _, r1 = best_ms(lambda: seq.score_argmax(pp), prot, 3)   # class-map pass + filter on every call
+    prot.set_class_cache(1)
     b, med, r2 = best_ms(lambda: seq.score_argmax(pp), prot, 3)   # class copy cached
     assert (r1["position"], r1["score"]) == (res["position"], res["score"]) == (r2["position"], r2["score"])
-    out["config3_protein"].update({"filter_first_call_kernel_ms": first_ms, "filter_first_call_gres_s": n / first_ms / 1e6,
+    out["config3_protein"].update({"filter_uncached_kernel_ms": first_ms, "filter_uncached_gres_s": n / first_ms / 1e6,
                                    "filter_cached_kernel_ms": b, "filter_cached_gres_s": n / b / 1e6,
                                    "filter_stats": prot.last_stats,
                                    "hbm_frac_of_measured_cached": n / b / 1e6 / 6555.5})
