@@ -243,3 +243,130 @@ impl<A: Alphabet> Threshold<f32, U32> for Pipeline<A, Cuda> {
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// Resident sequences and fused scans (what bulk callers -- the CLI job loop,
+// `Scanner` -- should use: the sequence is uploaded once, scores never leave
+// the GPU).  Not part of the reference's trait surface; a thin inherent API.
+
+#[allow(non_camel_case_types)]
+type lm_seq = c_void;
+
+extern "C" {
+    fn lm_seq_from_ascii(ctx: *mut lm_ctx, alphabet: c_int, ascii: *const u8, n: usize, lossy: c_int,
+                         wrap: usize, out: *mut *mut lm_seq, bad_index: *mut usize) -> c_int;
+    fn lm_seq_from_striped(ctx: *mut lm_ctx, alphabet: c_int, data: *const u8, rows: usize, wrap: usize,
+                           stride: usize, length: usize, out: *mut *mut lm_seq) -> c_int;
+    fn lm_seq_info(seq: *const lm_seq, alphabet: *mut c_int, rows: *mut usize, wrap: *mut usize,
+                   length: *mut usize) -> c_int;
+    fn lm_seq_free(ctx: *mut lm_ctx, seq: *mut lm_seq);
+    fn lm_seq_score_argmax_f32(ctx: *mut lm_ctx, seq: *const lm_seq, pssm: *const f32, m: usize,
+                               pssm_stride: usize, row_begin: usize, row_end: usize, rule: c_int,
+                               best: *mut LmHit, per_column: *mut c_void, first_cell: *mut f32) -> c_int;
+    fn lm_seq_score_threshold_f32(ctx: *mut lm_ctx, seq: *const lm_seq, pssm: *const f32, m: usize,
+                                  pssm_stride: usize, row_begin: usize, row_end: usize, t: f32,
+                                  hits: *mut LmHit, cap: usize, count: *mut usize) -> c_int;
+}
+
+const LM_RULE_SSE2: c_int = 2;
+
+/// A `StripedSequence` resident in GPU memory (cf. the `Arc<StripedSequence>` the CLI shares
+/// between its workers, lightmotif-cli/src/main.rs:540-562).
+pub struct CudaSequence<'p, A: Alphabet> {
+    pli: &'p Pipeline<A, Cuda>,
+    seq: *mut lm_seq,
+    rows: usize,
+    length: usize,
+}
+
+impl<A: Alphabet> Drop for CudaSequence<'_, A> {
+    fn drop(&mut self) {
+        unsafe { lm_seq_free(self.pli.backend().ctx, self.seq) }
+    }
+}
+
+impl<A: Alphabet> Pipeline<A, Cuda> {
+    /// `EncodedSequence::encode(text)?.to_striped()` + `configure_wrap(wrap)` in one device pass.
+    pub fn upload_ascii<S: AsRef<[u8]>>(&self, text: S, wrap: usize) -> Result<CudaSequence<'_, A>, InvalidSymbol> {
+        let s = text.as_ref();
+        let (mut seq, mut bad) = (std::ptr::null_mut(), 0usize);
+        match unsafe { lm_seq_from_ascii(self.backend().ctx, alphabet_tag::<A>(), s.as_ptr(), s.len(), 0, wrap, &mut seq, &mut bad) } {
+            LM_OK => Ok(self.adopt(seq)),
+            LM_ERR_INVALID_SYMBOL => Err(InvalidSymbol(s[bad] as char)),
+            e => panic!("lightmotif_b200: lm_seq_from_ascii failed with status {}", e),
+        }
+    }
+
+    /// Upload an existing (configured) `StripedSequence`.
+    pub fn upload(&self, striped: &StripedSequence<A, U32>) -> CudaSequence<'_, A> {
+        let m = striped.matrix();
+        let mut seq = std::ptr::null_mut();
+        let st = unsafe {
+            lm_seq_from_striped(self.backend().ctx, alphabet_tag::<A>(), m[0].as_ptr() as *const u8,
+                                m.rows() - striped.wrap(), striped.wrap(), m.stride(), striped.len(), &mut seq)
+        };
+        assert_eq!(st, LM_OK, "lightmotif_b200: lm_seq_from_striped failed");
+        self.adopt(seq)
+    }
+
+    fn adopt(&self, seq: *mut lm_seq) -> CudaSequence<'_, A> {
+        let (mut a, mut rows, mut wrap, mut length) = (0, 0usize, 0usize, 0usize);
+        unsafe { lm_seq_info(seq, &mut a, &mut rows, &mut wrap, &mut length) };
+        CudaSequence { pli: self, seq, rows, length }
+    }
+}
+
+impl<A: Alphabet> CudaSequence<'_, A> {
+    /// `pssm.score(&seq).argmax()` fused: `(position, score)` of the cell `Pipeline::dispatch()`
+    /// would return (AVX2 tie rule), bit-identical score.
+    pub fn score_argmax<M: AsRef<DenseMatrix<f32, A::K>>>(&self, pssm: M) -> Option<(usize, f32)> {
+        self.argmax_with_rule(pssm, LM_RULE_AVX2)
+    }
+
+    fn argmax_with_rule<M: AsRef<DenseMatrix<f32, A::K>>>(&self, pssm: M, rule: c_int) -> Option<(usize, f32)> {
+        let p = pssm.as_ref();
+        let mut best = LmHit::default();
+        let st = unsafe {
+            lm_seq_score_argmax_f32(self.pli.backend().ctx, self.seq, p[0].as_ptr(), p.rows(), p.stride(), 0, self.rows,
+                                    rule, &mut best, std::ptr::null_mut(), std::ptr::null_mut())
+        };
+        match st {
+            LM_OK => Some((best.position as usize, best.score)),
+            LM_EMPTY => None,
+            LM_ERR_WRAP => panic!("not enough wrapping rows for motif of length {}", p.rows()),
+            e => panic!("lightmotif_b200: lm_seq_score_argmax_f32 failed with status {}", e),
+        }
+    }
+
+    /// What `Scanner::new(pssm, seq).threshold(t).collect()` yields (scan.rs:169-198): every position
+    /// p with p + M <= len whose exact f32 score is >= t, sorted by position.
+    pub fn scan<M: AsRef<DenseMatrix<f32, A::K>>>(&self, pssm: M, t: f32) -> Vec<(usize, f32)> {
+        let p = pssm.as_ref();
+        let mut cap = 1024usize;
+        loop {
+            let mut hits = vec![LmHit::default(); cap];
+            let mut count = 0usize;
+            let st = unsafe {
+                lm_seq_score_threshold_f32(self.pli.backend().ctx, self.seq, p[0].as_ptr(), p.rows(), p.stride(), 0,
+                                           self.rows, t, hits.as_mut_ptr(), cap, &mut count)
+            };
+            match st {
+                LM_OK => {
+                    hits.truncate(count);
+                    let mut out: Vec<(usize, f32)> = hits.iter()
+                        .filter(|h| h.position as usize + p.rows() <= self.length)
+                        .map(|h| (h.position as usize, h.score)).collect();
+                    out.sort_by_key(|h| h.0);
+                    return out;
+                }
+                LM_ERR_OVERFLOW => cap = count,
+                e => panic!("lightmotif_b200: lm_seq_score_threshold_f32 failed with status {}", e),
+            }
+        }
+    }
+
+    /// `Scanner::max()` (scan.rs:200-249): best hit, ties towards the larger position.
+    pub fn scan_max<M: AsRef<DenseMatrix<f32, A::K>>>(&self, pssm: M) -> Option<(usize, f32)> {
+        self.argmax_with_rule(pssm, LM_RULE_SSE2)
+    }
+}
