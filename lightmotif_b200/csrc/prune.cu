@@ -42,7 +42,10 @@ namespace lm {
 
 namespace {
 
-constexpr int PW = 8;                   // consumer (filter) warps per CTA
+#ifndef LM_PRUNE_PW
+#define LM_PRUNE_PW 8
+#endif
+constexpr int PW = LM_PRUNE_PW;         // consumer (filter) warps per CTA
 constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #ifndef LM_PRUNE_G
 #define LM_PRUNE_G LM_PRUNE_PL  // rows per look-up block (operand reuse, accumulator ILP, one test per block)

@@ -37,4 +37,30 @@ enc = dna.encode(ascii_)
 assert np.array_equal(enc, sym)
 striped = dna.stripe(sym, 19)
 assert np.array_equal(striped, st)
-print("sanitize smoke ok", best)
+# many-motif job loop (argmax + per-motif thresholds) through the planner
+off = np.concatenate([[0], np.cumsum(z["widths"])])
+motifs = [z["counts"][off[i]:off[i + 1]] for i in range(len(z["widths"])) if 8 <= z["widths"][i] <= 20][:6]
+pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in motifs] + [pssm]
+dna.set_prune(2)
+bb = seq.score_argmax_batch(pssms)
+dna.set_prune(0)
+assert [b["position"] for b in bb] == [seq.score_argmax(p)["position"] for p in pssms]
+dna.set_prune(2)
+thr = [b["score"] - 2.0 for b in bb]
+hb = seq.score_threshold_batch(pssms, thr, cap=256)
+dna.set_prune(0)
+assert hb == [seq.score_threshold(p, t) for p, t in zip(pssms, thr)]
+# protein: class-coded filter, recheck from the residues in global memory
+prot = lm.Pipeline.cuda(lm.PROTEIN)
+pp = O.pssm_from_sequences(O.PROTEIN, ["SFKELGFDSLTAVELRNRLAAAT", "AFKELGFDSLAAIQLRNRLLADV", "PSRRLGFDSLTAVELRNQLAAST"], 0.1)[:15]
+psym = O.synth_protein(200_003)
+psym[::501] = 20
+pseq = prot.sequence_from_symbols(psym, 14)
+prot.set_boot_rows(512)
+prot.set_prune(0)
+e = pseq.score_argmax(pp)
+eh = pseq.score_threshold(pp, e["score"] - 6.0)
+prot.set_prune(2)
+assert pseq.score_argmax(pp) == e and prot.last_stats["pruned"]
+assert pseq.score_threshold(pp, e["score"] - 6.0) == eh
+print("sanitize smoke ok", best, e)
