@@ -35,11 +35,12 @@ METRIC = "Gbp/s scanned (width-20 DNA PSSM, fused score+argmax)"
 
 
 def rest_pssm():
-    """MA0138.3 REST counts -> to_freq(0.1).to_scoring(None): host-side O(M*K)
-    set-up using the same libm log2f as the reference (tests/golden fixture)."""
-    from oracle import oracle as O  # PSSM construction only (off the hot path)
+    """MA0138.3 REST counts -> to_freq(0.1).to_scoring(None): host-side O(M*K) set-up with the
+    harness's own constructors (lightmotif_b200/pwm.py, same libm log2f as the reference); the count
+    matrix comes from the JASPAR fixture."""
+    from lightmotif_b200 import pwm
     z = np.load(REPO / "tests" / "golden" / "jaspar2024.npz")
-    return O.pssm_from_counts(O.DNA, z["rest"], 0.1)
+    return pwm.pssm_from_counts(pwm.DNA, z["rest"], 0.1)
 
 
 def measured_traffic(per_gpu_bp, pruned):

@@ -1,5 +1,5 @@
 """Small end-to-end pass over every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
-  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+  compute-sanitizer --tool memcheck python tests/sanitize_smoke.py"""
 import sys
 from pathlib import Path
 import numpy as np

@@ -17,7 +17,7 @@ REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests"))
 import lightmotif_b200 as lm  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (PSSM construction + spot checks only)
+from lightmotif_b200 import pwm  # noqa: E402
 
 
 def best_ms(fn, pli, reps):
@@ -45,7 +45,7 @@ def main():
     from conftest import load_ecoli_codes
     codes = load_ecoli_codes()
     kat = json.loads((REPO / "tests/golden/kat.json").read_text())["dna"]
-    pssm = O.pssm_from_sequences(O.DNA, kat["patterns"], kat["pseudocount"])
+    pssm = pwm.pssm_from_sequences(pwm.DNA, kat["patterns"], kat["pseudocount"])
     seq = dna.sequence_from_symbols(codes, len(pssm) - 1)
     b, med, res = best_ms(lambda: seq.score_argmax(pssm), dna, 20)
     t0 = time.perf_counter()
@@ -63,7 +63,7 @@ def main():
 
     # ---- configs[2]: 1024 JASPAR motifs (widths 6..30) over 100 Mbp, per-motif argmax
     sel = [m for m in motifs if 6 <= len(m) <= 30][:1024]
-    pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in sel]
+    pssms = [pwm.pssm_from_counts(pwm.DNA, c, 0.1) for c in sel]
     n = 100_000_000 // scale
     maxw = max(len(p) for p in pssms)
     seq = dna.sequence_synthetic(n, maxw - 1)
@@ -102,7 +102,7 @@ def main():
 
     # ---- configs[3]: protein width-15 PSSM over 500 M residues
     pk = json.loads((REPO / "tests/golden/kat.json").read_text())["protein"]
-    pp = O.pssm_from_sequences(O.PROTEIN, pk["patterns"], pk["pseudocount"])[:15]
+    pp = pwm.pssm_from_sequences(pwm.PROTEIN, pk["patterns"], pk["pseudocount"])[:15]
     n = 500_000_000 // scale
     seq = prot.sequence_synthetic(n, 14)
     prot.set_prune(0)
@@ -126,7 +126,8 @@ def main():
 
     # ---- stage kernels: ASCII -> encode + stripe + wrap in one pass
     n = 1_000_000_000 // scale
-    ascii_ = np.frombuffer(b"ACTG", np.uint8)[O.synth_dna(min(n, 64_000_000))]
+    rng = np.random.default_rng(1)
+    ascii_ = np.frombuffer(b"ACTG", np.uint8)[rng.integers(0, 4, min(n, 64_000_000))]
     ascii_ = np.tile(ascii_, n // ascii_.size + 1)[:n].copy()
     t0 = time.perf_counter()
     s = dna.sequence_from_ascii(ascii_, 19)

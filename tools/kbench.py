@@ -12,7 +12,7 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import lightmotif_b200 as lm  # noqa: E402
-from oracle import oracle as O  # noqa: E402  (PSSM construction only)
+from lightmotif_b200 import pwm  # noqa: E402
 
 
 def main():
@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--thr", type=float, default=18.0)
     a = ap.parse_args()
     z = np.load(Path(__file__).resolve().parent.parent / "tests/golden/jaspar2024.npz")
-    pssm = O.pssm_from_counts(O.DNA, z["rest"], 0.1)
+    pssm = pwm.pssm_from_counts(pwm.DNA, z["rest"], 0.1)
     if a.m != 20:
         rng = np.random.default_rng(a.m)
         pssm = np.concatenate([pssm] * (a.m // 20 + 1))[: a.m].copy()
