@@ -434,7 +434,9 @@ int seq_alloc(lm_ctx* ctx, int alphabet, size_t rows, size_t wrap, size_t length
   s->wrap = wrap;
   s->length = length;
   s->alloc_rows = rows + wrap + SLACK_ROWS;
-  cudaError_t e = cudaMalloc((void**)&s->data, s->alloc_rows * 32);
+  // stream-ordered allocation from the device's default pool (kept warm: see lm_ctx_create): a caller
+  // that uploads, scans and frees sequence after sequence does not pay the OS for every cycle
+  cudaError_t e = cudaMallocAsync((void**)&s->data, s->alloc_rows * 32, ctx->stream);
   if (e != cudaSuccess) { delete s; return fail(ctx, e, "cudaMalloc(sequence)"); }
   *out = s;
   return LM_OK;
@@ -492,6 +494,14 @@ int lm_ctx_create_on_stream(int device, void* cuda_stream, lm_ctx** out) {
   }
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  {  // keep freed sequence buffers in the device's default memory pool instead of returning them to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   int s = ensure(ctx, ctx->d_small, SMALL_BYTES);
   if (s < 0) { lm_ctx_destroy(ctx); return s; }
   for (auto& sl : ctx->slots) {
@@ -930,14 +940,14 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
   if (seq->rows + wrap + SLACK_ROWS > seq->alloc_rows) {
     size_t new_alloc = seq->rows + wrap + SLACK_ROWS;
     uint8_t* nd = nullptr;
-    LM_TRY(cudaMalloc((void**)&nd, new_alloc * 32));
+    LM_TRY(cudaMallocAsync((void**)&nd, new_alloc * 32, ctx->stream));
     cudaError_t e = cudaMemcpyAsync(nd, seq->data, (seq->rows + seq->wrap) * 32, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(nd + (seq->rows + seq->wrap) * 32, pad_symbol(seq->alphabet),
                                               (new_alloc - seq->rows - seq->wrap) * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cudaFree(nd); return fail(ctx, e, "grow sequence"); }
+    if (e != cudaSuccess) { cudaFreeAsync(nd, ctx->stream); return fail(ctx, e, "grow sequence"); }
     if (ctx->class_src == seq->data) ctx->class_src = nullptr;
-    cudaFree(seq->data);
+    cudaFreeAsync(seq->data, ctx->stream);
     seq->data = nd;
     seq->alloc_rows = new_alloc;
   }
@@ -984,7 +994,10 @@ void lm_seq_free(lm_ctx* ctx, lm_seq* seq) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->class_src == seq->data) ctx->class_src = nullptr;  // the class-coded copy dies with its sequence
   }
-  if (seq->owned && seq->data) cudaFree(seq->data);
+  if (seq->owned && seq->data) {
+    if (ctx) cudaFreeAsync(seq->data, ctx->stream);
+    else cudaFree(seq->data);
+  }
   delete seq;
 }
 
