@@ -236,3 +236,59 @@ def test_protein_filter_equals_exact(prot, m, kind):
     e2 = seq2.score_argmax(pssm)
     prot.set_prune(2)
     assert seq2.score_argmax(pssm) == e2
+
+
+# ------------------------------------------------------------------ edge cases
+def test_long_motifs_and_limits(dna):
+    """Motifs at and beyond the filter's width limit (256 rows) and sub-range scans: the filter is used
+    where a plan exists, the exact kernel otherwise; results identical either way."""
+    rng = np.random.default_rng(11)
+    n = 2_000_003
+    sym = rng.integers(0, 4, n).astype(np.uint8)
+    sym[70_000:70_050] = 4
+    dna.set_boot_rows(2048)
+    for m in (64, 200, 256, 300):
+        counts = rng.integers(0, 30, size=(m, 5)).astype(np.uint32)
+        counts[:, 4] = 0
+        counts[np.arange(m), rng.integers(0, 4, m)] += 60
+        pssm = O.pssm_from_counts(O.DNA, counts, 0.1)
+        sym[500_000:500_000 + m] = np.argmax(pssm[:, :4], axis=1)  # one perfect site
+        seq = dna.sequence_from_symbols(sym, m - 1)
+        dna.set_prune(0)
+        exact = seq.score_argmax(pssm)
+        sub_exact = seq.score_argmax(pssm, rows=(1000, 40_000))
+        t = exact["score"] - 40.0
+        hits_exact = seq.score_threshold(pssm, t)
+        dna.set_prune(2)
+        assert seq.score_argmax(pssm) == exact
+        assert dna.last_stats["pruned"] == (1 if m <= 256 else 0)
+        assert seq.score_argmax(pssm, rows=(1000, 40_000)) == sub_exact
+        assert seq.score_threshold(pssm, t) == hits_exact and len(hits_exact) >= 1
+        dna.set_prune(0)
+        sub_hits = seq.score_threshold(pssm, t, rows=(15_000, 16_000))
+        dna.set_prune(2)
+        assert seq.score_threshold(pssm, t, rows=(15_000, 16_000)) == sub_hits
+        seq.free()
+    dna.set_prune(1)
+
+
+def test_all_default_symbols_and_minus_infinity(dna):
+    """A sequence of N only: every score is -inf; the fused calls still return the reference's cell."""
+    n = 700_001
+    sym = np.full(n, 4, np.uint8)
+    rng = np.random.default_rng(2)
+    pssm = random_pssm(rng, 12, "logodds")
+    seq = dna.sequence_from_symbols(sym, 11)
+    dna.set_boot_rows(1024)
+    dna.set_prune(0)
+    ref = seq.score(pssm)
+    assert np.all(np.isneginf(ref))
+    for r in (0, 1, 2):
+        dna.set_prune(0)
+        exact = seq.score_argmax(pssm, rule=r)
+        dna.set_prune(2)
+        got = seq.score_argmax(pssm, rule=r)
+        rr, cc = O.argmax(ref, r)
+        assert (got["row"], got["col"]) == (exact["row"], exact["col"]) == (rr, cc), r
+    dna.set_prune(2)
+    assert seq.score_threshold(pssm, 0.0) == []
