@@ -202,7 +202,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None) if "LM_NCCL_DEBUG" not in os.environ else os.environ.__setitem__("NCCL_DEBUG", os.environ["LM_NCCL_DEBUG"])  # NCCL_DEBUG prints its banner on stdout: keep stdout to the one JSON line
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        if "LM_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["LM_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
 
     per_gpu = args.bp_per_gpu
