@@ -8,9 +8,19 @@ scaling), reported with the HBM roofline of the scoring kernel and the CPU
 baseline (AVX2 restatement of the reference's path) timed beside it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL)
+  torchrun ... bench.py --gpus N ...            (one rank per GPU)
 
-One JSON line is printed by rank 0.
+One JSON line is printed by rank 0 (last line of stdout).  Besides the contract's keys it carries
+  roofline / cpu_baseline / e2e / clocks      as the task statement defines them
+  exact_everywhere                             the same scan with the filter disabled (result asserted equal)
+  sustained                                    the same steps repeated for >= --min-seconds
+  inputs                                       the same kernel on other 5 Gbp inputs (real genome tiled,
+                                               low-complexity + N runs, weak motif, fused threshold)
+  materialised                                 ScoringMatrix::score with StripedScores written to HBM
+  configs                                      BASELINE configs[2] (1024 motifs x 100 Mbp) and [3] (protein)
+  multi_gpu (N > 1)                            per-rank kernel times, the in-run check of the merged result
+                                               against an exact re-scan, and the NCCL all-gather exchange
+                                               timed on the same scans for comparison
 """
 from __future__ import annotations
 
@@ -32,6 +42,14 @@ WIDTH = 20
 PER_GPU_BP = 5_000_000_000
 SEED = 0x5EED
 METRIC = "Gbp/s scanned (width-20 DNA PSSM, fused score+argmax)"
+REF_SAMPLE_BP = 256_000_000
+
+
+def jaspar():
+    z = np.load(REPO / "tests" / "golden" / "jaspar2024.npz")
+    widths = z["widths"]
+    offs = np.concatenate([[0], np.cumsum(widths)])
+    return z, [z["counts"][offs[i]:offs[i + 1]] for i in range(len(widths))]
 
 
 def rest_pssm():
@@ -39,20 +57,20 @@ def rest_pssm():
     harness's own constructors (lightmotif_b200/pwm.py, same libm log2f as the reference); the count
     matrix comes from the JASPAR fixture."""
     from lightmotif_b200 import pwm
-    z = np.load(REPO / "tests" / "golden" / "jaspar2024.npz")
-    return pwm.pssm_from_counts(pwm.DNA, z["rest"], 0.1)
+    return pwm.pssm_from_counts(pwm.DNA, jaspar()[0]["rest"], 0.1)
 
 
 def measured_traffic(per_gpu_bp, pruned):
     """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/ncu_traffic.json); only when the capture is of this workload."""
+    (profiles/ncu_traffic.json).  NOT measured in this run: the capture is of the same workload and
+    kernel family; `capture` names it."""
     p = REPO / "profiles" / "ncu_traffic.json"
     if not (p.exists() and pruned):
-        return None
+        return None, None
     d = json.loads(p.read_text())
     if int(d.get("launch_bp", 0)) != int(per_gpu_bp):
-        return None
-    return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+        return None, None
+    return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"]), d.get("capture", "profiles/ncu_traffic.json")
 
 
 def measured_peaks():
@@ -72,9 +90,7 @@ class ClockSampler:
     * throttle reasons (and an NVML clock reading for cross-checking) are sampled through NVML
       immediately before the first and after the last timed step -- the GPU is hot from the warm-up
       steps -- and, on a single GPU, also inline between steps.  NVML calls are kept out of the
-      multi-GPU timed region: each one stalls the NCCL-coupled pipeline of both ranks by ~4 ms on
-      these hosts (measured: 10 steps went from 1.25 to 2.57 ms/step with three inline queries; a
-      2 ms polling thread cost 40 %)."""
+      multi-GPU timed region: each one stalls the coupled ranks by ~4 ms on these hosts."""
 
     BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
@@ -123,7 +139,7 @@ class ClockSampler:
                 "nvml_sm_mhz": self.nvml_mhz}
 
 
-def cpu_baseline(pssm, threads=None, target_s=10.0, sample_bp=256_000_000):
+def cpu_baseline(pssm, threads=None, target_s=10.0, sample_bp=REF_SAMPLE_BP):
     """The reference's AVX2 path (restated in oracle/lm_avx2_ref.c, the Rust
     crate cannot be built here) on the host cores: materialise StripedScores,
     then argmax -- pssm.score(&striped) + scores.argmax() -- row range split
@@ -147,7 +163,10 @@ def cpu_baseline(pssm, threads=None, target_s=10.0, sample_bp=256_000_000):
     return {"value": gbps, "unit": "Gbp/s", "cores": threads, "kind": "port",
             "sample": f"{passes} passes over the first {sample_bp / 1e6:.0f} Mbp of the workload "
                       f"({dt:.1f} s wall), AVX2 score (materialised) + argmax, {threads} threads",
-            "argmax": [int(res[1]), int(res[2])]}, dt / passes
+            "reference_sample_bp": sample_bp, "threads": threads,
+            "note": "rate on a 256 Mbp sample vs the GPU's rate on the full 5 Gbp (the reference is single-threaded "
+                    "per call; all host threads are used here, which favours the baseline)",
+            "argmax": [int(res[1]), int(res[2])]}
 
 
 def run_reference(args):
@@ -158,7 +177,7 @@ def run_reference(args):
     # each "step" = one pass over a bounded sample; K steps + W warm-up
     from oracle import oracle as O
     threads = os.cpu_count() or 1
-    sample_bp = 256_000_000
+    sample_bp = REF_SAMPLE_BP
     sym = O.synth_dna(sample_bp, 0, SEED)
     striped = O.stripe(O.DNA, sym, 32, WIDTH - 1)
     rows = striped.shape[0] - (WIDTH - 1)
@@ -179,13 +198,182 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "width-20 DNA PSSM (MA0138.3 REST) over 5 Gbp synthetic DNA, score+argmax",
-                   "sample_bp_per_step": sample_bp},
+                   "sample_bp_per_step": sample_bp,
+                   "note": "rate measured on a 256 Mbp sample per step (a bounded CPU run), compared with the GPU arm's "
+                           "rate on the full 5 Gbp"},
         "cpu_baseline": {"value": gbps, "unit": "Gbp/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
+
+# ------------------------------------------------------------------------------------------------
+# extra blocks (single GPU, rank 0)
+
+def best_kernel_ms(fn, pli, reps):
+    ts, r = [], None
+    for _ in range(reps):
+        r = fn()
+        ts.append(pli.last_kernel_ms)
+    return min(ts), float(np.median(ts)), r
+
+
+def scan_report(pli, seq, pssm, peak, reps=4, threshold=None):
+    """One fused scan of a 5 Gbp input through the same kernel as the headline."""
+    n = seq.rows * 32
+    if threshold is None:
+        b, med, res = best_kernel_ms(lambda: seq.score_argmax(pssm), pli, reps)
+        out = {"result": {"position": res["position"], "score": res["score"]}}
+    else:
+        b, med, res = best_kernel_ms(lambda: seq.score_threshold(pssm, threshold, cap=1 << 21, as_array=True), pli, reps)
+        out = {"hits": int(len(res)), "threshold": float(threshold)}
+    st = pli.last_stats
+    out.update({"gbp_s": n / med / 1e6, "kernel_ms": med, "kernel_ms_best": b, "frac_of_hbm_peak": n / med / 1e6 / peak,
+                "rechecked": st["rechecked"], "overflow_tiles": st["overflow_tiles"],
+                "filter": (f"{'paired' if st['paired'] else 'single'} x{st['filter_rows']}" if st["pruned"] else "none (exact kernel)")})
+    return out
+
+
+def inputs_block(pli, pssm, per_gpu, peak, jas):
+    """The headline kernel on inputs that are less friendly than uniform-random DNA + a strong motif."""
+    import lightmotif_b200 as lm
+    from lightmotif_b200 import pwm
+    sys.path.insert(0, str(REPO / "tests"))
+    from conftest import load_ecoli_codes
+    out = {}
+    wrap = WIDTH - 1
+    # (i) a real genome: E. coli K12 (4.64 Mbp, tests/golden) tiled to the workload's length
+    codes = load_ecoli_codes()
+    reps = -(-per_gpu // codes.size)
+    tiled = np.tile(codes, reps)[:per_gpu]
+    seq = pli.sequence_from_symbols(tiled, wrap)
+    del tiled
+    out["ecoli_tiled"] = scan_report(pli, seq, pssm, peak)
+    out["ecoli_tiled"]["input"] = f"E. coli K12 genome (4 641 652 bp) repeated {reps}x to {per_gpu / 1e9:g} Gbp; every maximum recurs in each copy (ties)"
+    seq.free()
+    # (ii) synthetic DNA with 5 % of the positions inside low-complexity runs (poly-A, (AC)n, (GT)n) and N runs
+    syn = pli.sequence_synthetic(per_gpu, wrap, seed=SEED)
+    host = syn.download()
+    rows = syn.rows
+    rng = np.random.default_rng(7)
+    run, n_runs = 1000, int(0.05 * per_gpu / 1000)
+    cols = rng.integers(0, 32, n_runs)
+    starts = rng.integers(64, rows - run - 64, n_runs)
+    kinds = rng.integers(0, 4, n_runs)
+    pat = [np.zeros(run, np.uint8), np.tile(np.array([0, 1], np.uint8), run // 2),
+           np.tile(np.array([3, 2], np.uint8), run // 2), np.full(run, 4, np.uint8)]
+    for c, r0, k in zip(cols.tolist(), starts.tolist(), kinds.tolist()):
+        host[r0:r0 + run, c] = pat[k]
+    host[rows:rows + wrap, :31] = host[:wrap, 1:]  # wrap rows follow the (unchanged) first rows
+    low = pli.sequence_from_striped(host, per_gpu, wrap)
+    del host
+    out["low_complexity_5pct"] = scan_report(pli, low, pssm, peak)
+    out["low_complexity_5pct"]["input"] = (f"synthetic DNA with {n_runs} runs of {run} bp (5 % of the positions): poly-A, (AC)n, (GT)n "
+                                           "and N runs in equal parts")
+    low.free()
+    # (iii) the weakest motif of the many-motif set (lowest information content, widths 6..20) on the synthetic input
+    cands = [c for c in jas if 6 <= len(c) <= WIDTH][:1024]
+
+    def info(c):
+        f = pwm.to_freq(pwm.DNA, c, 0.1)[:, :4].astype(np.float64)
+        return float(np.sum(2.0 + np.sum(np.where(f > 0, f * np.log2(np.maximum(f, 1e-300)), 0.0), axis=1)))
+    weak = min(cands, key=info)
+    wp = pwm.pssm_from_counts(pwm.DNA, weak, 0.1)
+    out["weak_motif"] = scan_report(pli, syn, wp, peak)
+    out["weak_motif"]["input"] = f"synthetic DNA; lowest-information motif of the 1024-motif set: width {len(weak)}, {info(weak):.2f} bits"
+    # (iv) fused score + threshold (the device Scanner) at the score a fraction 1e-4 of the positions reach
+    sample = seq_sample_scores(syn, pssm)
+    t = float(np.partition(sample, sample.size - int(1e-4 * sample.size))[sample.size - int(1e-4 * sample.size)])
+    out["threshold_p1e-4"] = scan_report(pli, syn, pssm, peak, reps=3, threshold=t)
+    out["threshold_p1e-4"]["input"] = "synthetic DNA, REST PSSM, all positions scoring >= the empirical 1 - 1e-4 quantile"
+    syn.free()
+    return out
+
+
+def seq_sample_scores(seq, pssm, rows=1 << 20):
+    s = seq.score(pssm, rows=(0, min(rows, seq.rows)))
+    s = s.reshape(-1)
+    return s[np.isfinite(s)]
+
+
+def materialised_block(pli, seq, pssm, peak):
+    """ScoringMatrix::score with the StripedScores matrix written to HBM (1 B read + 4 B written per
+    position): the reference README's headline operation."""
+    import torch
+    rows = seq.rows
+    out = torch.empty((rows, 32), dtype=torch.float32, device="cuda")
+    ts = []
+    for _ in range(3):
+        seq.score_into_device(pssm, out.data_ptr())
+        ts.append(pli.last_kernel_ms)
+    ms = float(np.median(ts[1:]))
+    n = rows * 32
+    # spot check: the first rows against the fused path's own exact scores
+    head = out[:4096].cpu().numpy()
+    want = seq.score(pssm, rows=(0, 4096))
+    assert np.array_equal(head.view(np.uint32), want.view(np.uint32))
+    del out
+    torch.cuda.empty_cache()
+    return {"gbp_s": n / ms / 1e6, "kernel_ms": ms, "bytes_per_position": 5,
+            "roofline": {"bound": "hbm", "achieved": 5.0 * n / ms / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": 5.0 * n / ms / 1e6 / peak},
+            "kernel": "lm::score_kernel<16, MODE_STORE, f32> (exact sequential f32 sum at every cell)",
+            "api": "lm_seq_score_f32(out_is_device = 1)"}
+
+
+def configs_block(peak, jas):
+    """BASELINE configs[2] (1024 JASPAR motifs over 100 Mbp, per-motif argmax) and configs[3]
+    (protein, width-15 PSSM over 500 M residues), through the C ABI, device-resident."""
+    import lightmotif_b200 as lm
+    from lightmotif_b200 import pwm
+    out = {}
+    dna = lm.Pipeline.cuda(lm.DNA)
+    sel = [m for m in jas if 6 <= len(m) <= 30][:1024]
+    pssms = [pwm.pssm_from_counts(pwm.DNA, c, 0.1) for c in sel]
+    n = 100_000_000
+    seq = dna.sequence_synthetic(n, max(len(p) for p in pssms) - 1, seed=SEED)
+    seq.score_argmax_batch(pssms)  # warm-up (plans cached per motif set)
+    walls, kms = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = seq.score_argmax_batch(pssms)
+        walls.append(time.perf_counter() - t0)
+        kms.append(dna.last_kernel_ms)
+    cells = float(n) * len(pssms)
+    out["config2_many_motifs"] = {
+        "workload": f"{len(pssms)} JASPAR PSSMs (widths 6-30) x {n / 1e6:g} Mbp synthetic DNA, per-motif argmax, one call",
+        "call_ms_wall": float(np.median(walls)) * 1e3, "kernel_ms": float(np.median(kms)),
+        "gcells_s_wall": cells / float(np.median(walls)) / 1e9, "motifs_through_filter": int(dna.last_stats["pruned"]),
+        "api": "lm_seq_score_argmax_f32_batch"}
+    for i in (0, len(pssms) // 2, len(pssms) - 1):  # spot check against single calls
+        single = seq.score_argmax(pssms[i])
+        assert (single["position"], single["score"]) == (res[i]["position"], res[i]["score"]), (i, single, res[i])
+    seq.free()
+    dna.close()
+    prot = lm.Pipeline.cuda(lm.PROTEIN)
+    pk = json.loads((REPO / "tests/golden/kat.json").read_text())["protein"]
+    pp = pwm.pssm_from_sequences(pwm.PROTEIN, pk["patterns"], pk["pseudocount"])[:15]
+    n = 500_000_000
+    seq = prot.sequence_synthetic(n, 14, seed=SEED)
+    prot.set_class_cache(0)
+    b, med, res = best_kernel_ms(lambda: seq.score_argmax(pp), prot, 4)
+    st = prot.last_stats
+    prot.set_prune(0)
+    be, mede, rese = best_kernel_ms(lambda: seq.score_argmax(pp), prot, 2)
+    assert (res["position"], res["score"]) == (rese["position"], rese["score"])
+    out["config3_protein"] = {
+        "workload": f"width-15 protein PSSM (benches/score.rs ACP motif) x {n / 1e6:g} M synthetic residues, fused argmax",
+        "gres_s": n / med / 1e6, "kernel_ms": med, "frac_of_hbm_peak": n / med / 1e6 / peak,
+        "exact_everywhere_gres_s": n / mede / 1e6, "rechecked": st["rechecked"], "pruned": st["pruned"],
+        "note": "class-cache disabled: every call pays for everything it needs (no reuse of a class-coded copy)",
+        "result": {"position": res["position"], "score": res["score"]}}
+    seq.free()
+    prot.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 
 def run_ours(args):
     import torch
@@ -202,11 +390,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
+        # torch.distributed / NCCL is the plumbing (rendezvous, handle exchange, barriers, the max over
+        # ranks of the timing).  NCCL_DEBUG is left exactly as the caller set it (its log lines share
+        # stdout; the JSON line is printed last, after the process group is gone).
         if "LM_NCCL_DEBUG" in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ["LM_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
 
     per_gpu = args.bp_per_gpu
@@ -218,36 +406,38 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)  # the library enqueues on this stream; events are recorded on it
     torch.cuda.set_stream(stream)
     pli = lm.Pipeline.cuda(lm.DNA, device=local, stream=stream.cuda_stream)
-    # this rank's row slab of the global striped matrix, generated in HBM
-    seq = pli.sequence_synthetic(total, WIDTH - 1, seed=SEED, row_begin=r0, n_rows=r1 - r0)
+    comm = None
+    if world > 1:
+        # the ranks' exchange buffers are mapped into each other (cudaIpc handles travel through
+        # torch.distributed once); from here on the GPUs talk through peer memory only
+        comm = lm.Comm.from_process_group(pli)
+        seq = comm.sequence_synthetic(total, WIDTH - 1, seed=SEED)[0]
+    else:
+        seq = pli.sequence_synthetic(total, WIDTH - 1, seed=SEED)
+    assert seq.rows == r1 - r0
     positions = (r1 - r0) * 32  # cells scored per step on this rank (1 byte each)
 
-    xchg = lmdist.WinnerExchange(device=dev) if world > 1 else None
-    row_offsets = [rows_global * r // world for r in range(world)]
-    if world > 1 and args.reserve_sms:
-        pli.set_reserve_sms(args.reserve_sms)  # room for the NCCL kernel of scan k beside scan k + 1
-
-    # One step = one fused scan of this rank's slab + (N > 1) the exchange of the winners: an NCCL
-    # all-gather of the 272-byte result block straight from HBM, enqueued on the scan's stream, and
-    # the tie-rule merge on the host.  Steps are software-pipelined `depth` deep: scans k+1 .. k+depth
-    # are enqueued before the host waits for scan k (so a late rank or a slow host thread does not
-    # idle the other GPUs).
+    # One step = one fused scan of this rank's slab; at N > 1 a row-sharded scan through the
+    # communicator: the scan kernels share their running maximum over NVLink while they run and hand
+    # their result blocks to every rank when they finish; the host merges with the tie rule.  Steps
+    # are software-pipelined `depth` deep over 4 launch slots.
     NSLOT = 4
-    depth = args.depth  # scans enqueued ahead of the one the host waits for (< NSLOT)
+    depth = args.depth
 
     def launch(k):
-        seq.score_argmax_launch(pssm, slot=k % NSLOT)
-        if world > 1:
-            xchg.enqueue(pli.result_block_ptr(k % NSLOT), slot=k % NSLOT)
+        if comm is not None:
+            comm.score_argmax_launch([seq], pssm, slot=k % NSLOT)
+        else:
+            seq.score_argmax_launch(pssm, slot=k % NSLOT)
 
     def finish(k):
-        res = seq.score_argmax_finish(slot=k % NSLOT, rule=lm.RULE_AVX2)
-        kms = pli.last_kernel_ms
-        if world > 1:  # global argmax over all slabs (every rank computes the same cell)
-            res = xchg.finish(k % NSLOT, row_offsets, rows_global, lm.RULE_AVX2)
-        return res, kms
+        if comm is not None:
+            res = comm.score_argmax_finish(slot=k % NSLOT, rule=lm.RULE_AVX2)
+        else:
+            res = seq.score_argmax_finish(slot=k % NSLOT, rule=lm.RULE_AVX2)
+        return res, pli.last_kernel_ms
 
-    def run_steps(n, sampler=None):
+    def run_steps(n, sampler=None, launch=launch, finish=finish):
         out = []
         for j in range(min(depth, n)):
             launch(j)
@@ -267,35 +457,87 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(n, sampler=None, **kw):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        results = run_steps(n, sampler, **kw)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, results
+
     run_steps(max(args.warmup, 1))
     stats = pli.last_stats
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = pli.kernel_launches
     if sampler is not None:
         sampler.sample_nvml()  # before the barrier: the stall an NVML query causes is over when timing starts
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    results = run_steps(args.steps, sampler)
-    e1.record(stream)
-    torch.cuda.synchronize()
+    ms, results = timed(args.steps, sampler)
     if sampler is not None:
         sampler.sample_nvml()
     sync_all()
     clocks = sampler.result() if rank == 0 else None
     res = results[-1][0]
     kernel_ms = [r[1] for r in results]
-    ms = e0.elapsed_time(e1)
     launches = pli.kernel_launches - launches0
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         lt = torch.tensor([launches], dtype=torch.float64, device=dev)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3) / 1e9  # whole-job Gbp/s
+
+    # ---- sustained: the same steps for >= min_seconds
+    sustained = None
+    if args.min_seconds > 0:
+        n_long = max(args.steps, int(args.min_seconds * 1e3 / ms_per_step) + 1)
+        ms_long, _ = timed(n_long)
+        sustained = {"seconds": ms_long / 1e3, "steps": n_long, "ms_per_step": ms_long / n_long,
+                     "value": total / (ms_long / n_long * 1e-3) / 1e9, "unit": "Gbp/s"}
+
+    # ---- N > 1: per-rank kernel times; the merged result against an exact re-scan of every slab;
+    # the NCCL all-gather exchange timed on the same scans
+    multi = None
+    if world > 1:
+        km = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+        allk = [torch.zeros_like(km) for _ in range(world)]
+        dist.all_gather(allk, km)
+        pli.set_prune(0)  # exact f32 sum at every cell of every slab; blocks published by lm::publish_kernel
+        exact_res = comm.score_argmax([seq], pssm, rule=lm.RULE_AVX2)
+        exact_ms = pli.last_kernel_ms
+        pli.set_prune(1)
+        assert exact_res == res, (rank, exact_res, res)
+        generic = comm.score_argmax([seq], pssm, rule=lm.RULE_GENERIC)
+        xchg = lmdist.WinnerExchange(device=dev)
+        row_offsets = [rows_global * r // world for r in range(world)]
+
+        def nccl_launch(k):
+            seq.score_argmax_launch(pssm, slot=k % NSLOT)
+            xchg.enqueue(pli.result_block_ptr(k % NSLOT), slot=k % NSLOT)
+
+        def nccl_finish(k):
+            seq.score_argmax_finish(slot=k % NSLOT, rule=lm.RULE_AVX2)
+            kms = pli.last_kernel_ms
+            return xchg.finish(k % NSLOT, row_offsets, rows_global, lm.RULE_AVX2), kms
+
+        run_steps(3, launch=nccl_launch, finish=nccl_finish)
+        nccl_ms, nccl_results = timed(args.steps, launch=nccl_launch, finish=nccl_finish)
+        assert nccl_results[-1][0] == res, (rank, nccl_results[-1][0], res)
+        multi = {"kernel_ms_per_rank": [float(t.item()) for t in allk],
+                 "exchange": "peer-mapped HBM (cudaIpc): running maximum shared with system-scope atomicMax during the "
+                             "scan, result blocks written to every rank by the scan kernel's last warp, arrival flags",
+                 "checked": {"exact_rescan_equal": True, "exact_rescan_kernel_ms": exact_ms,
+                             "nccl_path_equal": True, "generic_rule_result": generic},
+                 "nccl_allgather_baseline": {"ms_per_step": nccl_ms / args.steps,
+                                             "value": total / (nccl_ms / args.steps * 1e-3) / 1e9,
+                                             "kernel_ms": float(np.mean([r[1] for r in nccl_results])),
+                                             "note": "the round-1 exchange on the same scans: per-scan ncclAllGather of the "
+                                                     "272-byte blocks, no shared maximum"}}
 
     # ---- the same scan with the filter disabled (every cell gets the exact f32 sum), for reference
     exact = None
@@ -311,9 +553,15 @@ def run_ours(args):
         ex_ms = float(np.median(ems[1:]))
         exact = {"value": positions / (ex_ms * 1e-3) / 1e9, "unit": "Gbp/s (per GPU)", "kernel_ms": ex_ms,
                  "kernel": "lm::score_kernel<16, MODE_ARGMAX, f32> (LM_OPT_PRUNE=0: exact f32 sum at every cell)",
-                 "same_result": True}
+                 "same_result": world == 1}
     if world > 1:
         dist.barrier()
+
+    peak, how = measured_peaks()
+    extras = {}
+    if world == 1 and not args.no_extras:
+        jas = jaspar()[1]
+        extras["materialised"] = materialised_block(pli, seq, pssm, peak)
 
     # ---- end to end through the C ABI with HOST buffers (rank-local slab)
     e2e = None
@@ -326,8 +574,12 @@ def run_ours(args):
         seq.free()  # the resident copy is not used by the e2e path
 
         def e2e_step():
-            s = pli.sequence_from_striped(harr, total, WIDTH - 1)   # H2D of this step's input
-            r = s.score_argmax(pssm, rule=lm.RULE_AVX2)              # kernel + D2H of the result
+            if comm is not None:
+                s = pli.sequence_from_striped_slab(harr, total, WIDTH - 1, r0)   # H2D of this step's input
+                r = comm.score_argmax([s], pssm, rule=lm.RULE_AVX2)              # sharded scan + result to the host
+            else:
+                s = pli.sequence_from_striped(harr, total, WIDTH - 1)
+                r = s.score_argmax(pssm, rule=lm.RULE_AVX2)
             s.free()
             return r
 
@@ -346,15 +598,24 @@ def run_ours(args):
             dt = float(t.item())
         e2e = {"value": total / (dt / n_e2e) / 1e9, "unit": "Gbp/s",
                "h2d_bytes_per_step": int(harr.nbytes) * world + int(pssm.nbytes) * world,
-               "d2h_bytes_per_step": 272 * world,
-               "steps": n_e2e, "api": "lm_seq_from_striped(pinned host StripedSequence) + lm_seq_score_argmax_f32"}
-        if world == 1:
-            assert r_e2e["position"] == res["position"], (r_e2e, res)
+               "d2h_bytes_per_step": 272 if world == 1 else (320 + 320 * world + 8) * world,
+               "steps": n_e2e,
+               "api": ("lm_seq_from_striped(pinned host StripedSequence) + lm_seq_score_argmax_f32" if world == 1 else
+                       "lm_seq_from_striped_slab(pinned host slab) + lm_comm_score_argmax_f32_launch / _finish")}
+        assert r_e2e["position"] == res["position"], (r_e2e, res)
+        del host, harr
+    else:
+        seq.free()
 
+    if world == 1 and rank == 0 and not args.no_extras:
+        extras["inputs"] = inputs_block(pli, pssm, per_gpu, peak, jas)
+        extras["configs"] = configs_block(peak, jas)
+
+    line = None
     if rank == 0:
-        peak, how = measured_peaks()
         k_ms = float(np.mean(kernel_ms))
         achieved = positions * 1.0 / (k_ms * 1e-3) / 1e9  # GB/s of algorithmic bytes, per GPU
+        traffic, capture = measured_traffic(per_gpu, stats["pruned"])
         line = {
             "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -366,29 +627,41 @@ def run_ours(args):
                 "l2": "input per GPU (5 GB) exceeds L2 (126 MB); no flush needed",
                 "method": "LM_OPT_PRUNE=auto: integer upper bound for every cell (PRMT byte-lane look-ups, 4 cells per "
                           "instruction), exact sequential f32 sum only where the bound reaches the running maximum; "
-                          "result bit-identical to scoring every cell (checked in-run against exact_everywhere)",
-                "parallelism": f"row-sharded x{world}, NCCL all-gather of the 272-byte winner blocks (device-resident)" if world > 1 else "1 GPU",
+                          "result bit-identical to scoring every cell (checked in-run against an exact re-scan)",
+                "parallelism": (f"row-sharded x{world}; running maximum and result blocks exchanged through peer-mapped HBM "
+                                "over NVLink (no collective kernel); torch.distributed/NCCL for rendezvous and timing only")
+                               if world > 1 else "1 GPU",
                 "result": {"position": res["position"], "score": res["score"]},
+                "note": "cpu_baseline / the reference arm are rates on a 256 Mbp sample (bounded CPU run)",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(per_gpu, stats["pruned"]),
-                         "traffic_source": "profiles/ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "launch, ncu --set full)", "peak_source": how,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_measured_in_run": False, "traffic_capture": capture,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+                                           "(committed capture of this workload, not re-measured in this run)",
+                         "peak_source": how,
                          "kernel": (f"lm::prune_kernel<{stats['filter_rows']}, {'paired' if stats.get('paired') else 'single'}, argmax> (exact filter + recheck; "
                                     "+ lm::score_kernel on the first 262144 rows)") if stats["pruned"]
                          else "lm::score_kernel<16, MODE_ARGMAX, f32>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": positions,
                          "filter": stats},
-            "exact_everywhere": exact,
+            "exact_everywhere": exact, "sustained": sustained,
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
         }
+        if multi is not None:
+            line["multi_gpu"] = multi
+        line.update(extras)
         if world == 1 and not args.no_cpu:
-            cb, _ = cpu_baseline(pssm)
-            line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline"] = cpu_baseline(pssm)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(0.5)  # let the other ranks' NCCL log lines drain before the JSON line
+    if line is not None:
+        sys.stdout.write("\n" + json.dumps(line) + "\n")
+        sys.stdout.flush()
 
 
 def main():
@@ -398,11 +671,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--bp-per-gpu", type=int, default=PER_GPU_BP)
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="length of the sustained measurement (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the inputs / materialised / configs blocks")
     ap.add_argument("--depth", type=int, default=2, choices=[1, 2, 3], help="scans enqueued ahead of the host")
-    ap.add_argument("--reserve-sms", type=int, default=0, help="N > 1: SMs the scan grid leaves free for the NCCL kernel")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

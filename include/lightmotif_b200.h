@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LM_ABI_VERSION 1
+#define LM_ABI_VERSION 2
 #define LM_LANES 32 /* <Avx2 as Backend>::Lanes = U32, avx2.rs:33-35 */
 
 /* status codes */
@@ -215,6 +215,15 @@ int lm_seq_from_symbols(lm_ctx *ctx, int alphabet, const uint8_t *sym, size_t n,
 int lm_seq_from_striped(lm_ctx *ctx, int alphabet, const uint8_t *data,
                         size_t rows, size_t wrap, size_t stride, size_t length,
                         lm_seq **out);
+/* upload a ROW SLAB of a longer host StripedSequence: `data` points at row
+ * `row_offset` of a striped matrix with `rows_global` = ceil(length / 32) rows;
+ * the slab holds `rows` rows followed by `halo` rows (the NEXT rows of that
+ * matrix, or its wrap rows for the last slab).  Hits / positions of scans over
+ * the slab are reported in the coordinates of the whole matrix; the handle can
+ * be passed to the lm_comm_* calls of the rank that owns it. */
+int lm_seq_from_striped_slab(lm_ctx *ctx, int alphabet, const uint8_t *data,
+                             size_t rows, size_t halo, size_t stride, size_t length,
+                             uint64_t row_offset, uint64_t rows_global, lm_seq **out);
 /* adopt caller-owned DEVICE memory holding [rows + wrap][32] bytes (16-byte
  * aligned, row stride 32); the handle does not free it */
 int lm_seq_from_device(lm_ctx *ctx, int alphabet, void *device_ptr, size_t rows,
@@ -359,6 +368,75 @@ int lm_plan_filter_protein(const float *pssm, size_t m, size_t pssm_stride,
 int lm_argmax_merge(const lm_colwin *parts, size_t n_parts,
                     const uint64_t *row_offsets, float first_cell,
                     uint64_t total_rows, int rule, lm_hit *best);
+
+/* ------------------------------------------------ multi-GPU (row-sharded) scans
+ *
+ * The reference has no multi-device path; its sharding axis is the row range of
+ * Score::score_rows_into (pli/mod.rs:72-77).  A communicator couples `world`
+ * ranks (one GPU each): rank g scans rows [rows * g / world, rows * (g+1) / world)
+ * of the global striped matrix (+ halo rows).  During a fused argmax scan the GPUs
+ * share their running maximum through peer-mapped HBM (system-scope atomicMax over
+ * NVLink), so every GPU filters at the global maximum; at the end of a scan the
+ * scan kernel itself writes the rank's result block into every rank's memory and
+ * raises an arrival flag.  No collective library is involved.  Results are the
+ * cell / the hit list ONE call over the whole matrix would return (same tie rules,
+ * positions = col * rows_global + row).
+ *
+ * lm_comm_init:        ONE process drives `n_dev` GPUs (devices[i] or 0..n_dev-1;
+ *                      the same device may be listed twice, e.g. for testing).
+ *                      LM_ERR_UNSUPPORTED when two devices cannot address each
+ *                      other's memory.
+ * lm_comm_init_rank:   one process per GPU: creates this rank's exchange buffer on
+ *                      ctx's device and returns its cudaIpc handle; exchange the
+ *                      handles by any means (MPI, torch.distributed, a file) and
+ *                      pass all `world` of them, in rank order, to lm_comm_connect.
+ * All ranks must issue the same sequence of sharded calls (like any collective).
+ * `hit_capacity` = hits per rank a sharded threshold scan can hold (0: 1 << 20). */
+#define LM_MAX_RANKS 16
+#define LM_COMM_HANDLE_BYTES 64
+typedef struct lm_comm lm_comm;
+int lm_comm_init(int n_dev, const int *devices, size_t hit_capacity, lm_comm **out);
+int lm_comm_init_rank(lm_ctx *ctx, int rank, int world, size_t hit_capacity,
+                      uint8_t handle_out[LM_COMM_HANDLE_BYTES], lm_comm **out);
+int lm_comm_connect(lm_comm *comm, const uint8_t *handles /* [world][LM_COMM_HANDLE_BYTES] */);
+void lm_comm_destroy(lm_comm *comm);
+const char *lm_comm_last_error(const lm_comm *comm);
+int lm_comm_world(const lm_comm *comm);
+/* ranks driven by this process (n_dev for lm_comm_init, 1 for lm_comm_init_rank) */
+int lm_comm_n_local(const lm_comm *comm);
+lm_ctx *lm_comm_ctx(lm_comm *comm, int local_index);
+int lm_comm_rank(const lm_comm *comm, int local_index);
+/* Row slabs of the local ranks: slabs[i] (i < lm_comm_n_local) is created on
+ * lm_comm_ctx(comm, i).  From a host StripedSequence ([rows + wrap][stride]; the
+ * halo of a slab is the next `wrap` rows of that matrix) or from the synthetic
+ * generator (lm_seq_synthetic).  Free each with lm_seq_free(lm_comm_ctx(comm, i), .). */
+int lm_comm_shard_from_striped(lm_comm *comm, int alphabet, const uint8_t *data,
+                               size_t rows, size_t wrap, size_t stride,
+                               size_t length, lm_seq **slabs);
+int lm_comm_seq_synthetic(lm_comm *comm, int alphabet, uint64_t seed,
+                          uint64_t total_length, size_t wrap, lm_seq **slabs);
+/* Row-sharded lm_seq_score_argmax_f32 (ScoringMatrix::score + StripedScores::argmax
+ * over the whole matrix).  launch enqueues the scans of the local ranks on their
+ * contexts' streams (0 <= slot < LM_SLOTS, several may be in flight); finish waits
+ * for the blocks of ALL ranks and returns the global cell on every rank. */
+int lm_comm_score_argmax_f32_launch(lm_comm *comm, const lm_seq *const *slabs,
+                                    const float *pssm, size_t m, size_t pssm_stride,
+                                    int slot);
+int lm_comm_score_argmax_f32_finish(lm_comm *comm, int slot, int rule, lm_hit *best);
+/* launch + finish on slot 0 */
+int lm_seq_score_argmax_f32_sharded(lm_comm *comm, const lm_seq *const *slabs,
+                                    const float *pssm, size_t m, size_t pssm_stride,
+                                    int rule, lm_hit *best);
+/* Row-sharded lm_seq_score_threshold_f32: every rank returns the COMPLETE hit list
+ * (rows / positions of the global matrix, row-major order, pli/mod.rs:210-221):
+ * the per-rank lists are gathered over NVLink straight out of the ranks' exchange
+ * buffers.  *count = total number of hits, local_counts (nullable, [world]) = hits
+ * found by each rank.  LM_ERR_OVERFLOW if *count > cap or a rank found more than
+ * the communicator's hit_capacity. */
+int lm_seq_score_threshold_f32_sharded(lm_comm *comm, const lm_seq *const *slabs,
+                                       const float *pssm, size_t m, size_t pssm_stride,
+                                       float t, lm_hit *hits, size_t cap, size_t *count,
+                                       size_t *local_counts);
 
 #ifdef __cplusplus
 }

@@ -20,9 +20,9 @@ from . import capi
 from .capi import (DNA, PROTEIN, RULE_AVX2, RULE_GENERIC, RULE_SSE2, LANES, ColWin, Hit,
                    LightmotifError)
 
-__all__ = ["Pipeline", "DeviceSequence", "InvalidSymbol", "UnsupportedBackend", "MatrixCoordinates",
+__all__ = ["Pipeline", "DeviceSequence", "Comm", "InvalidSymbol", "UnsupportedBackend", "MatrixCoordinates",
            "DNA", "PROTEIN", "RULE_GENERIC", "RULE_AVX2", "RULE_SSE2", "LANES", "alphabet_k",
-           "pad_pssm", "aligned_empty", "argmax_merge", "COLWIN_DTYPE"]
+           "pad_pssm", "aligned_empty", "argmax_merge", "COLWIN_DTYPE", "HIT_DTYPE"]
 
 
 class InvalidSymbol(ValueError):
@@ -192,18 +192,23 @@ class DeviceSequence:
             res["first_cell"] = float(np.float32(fc.value))
         return res
 
-    def score_threshold(self, pssm, t, rows=None, cap=1 << 20):
-        """Fused score + Threshold::threshold -> list of hits in row-major order."""
+    def score_threshold(self, pssm, t, rows=None, cap=1 << 20, as_array=False):
+        """Fused score + Threshold::threshold -> list of hits in row-major order (as_array: a numpy
+        array of HIT_DTYPE records instead of a list of dicts)."""
         p, stride = pad_pssm(pssm, self.alphabet)
         b, e = self._rng(rows)
-        hits = (Hit * cap)()
+        hits = np.zeros(cap, dtype=HIT_DTYPE)
         count = C.c_size_t(0)
         st = capi.lib().lm_seq_score_threshold_f32(self._pli._ctx, self._h, _ptr(p), p.shape[0], stride, b, e,
-                                                   float(t), hits, cap, C.byref(count))
+                                                   float(t), hits.ctypes.data_as(C.POINTER(Hit)), cap, C.byref(count))
         if st == capi.ERR_OVERFLOW:
-            return self.score_threshold(pssm, t, rows, cap=count.value)
+            return self.score_threshold(pssm, t, rows, cap=count.value, as_array=as_array)
         self._pli._check(st)
-        return [_hit(hits[i]) for i in range(count.value)]
+        hits = hits[:count.value]
+        if as_array:
+            return hits
+        return [{"row": int(h["row"]), "col": int(h["col"]), "position": int(h["position"]),
+                 "score": float(h["score"])} for h in hits]
 
     def _flatten(self, pssms):
         k = alphabet_k(self.alphabet)
@@ -315,9 +320,17 @@ class Pipeline:
     def cuda(cls, alphabet=DNA, device=0, stream=None):
         return cls(alphabet, device, stream)
 
+    @classmethod
+    def _borrow(cls, ctx, alphabet):
+        """Wrap a context owned by someone else (the ranks of an lm_comm)."""
+        self = cls.__new__(cls)
+        self.alphabet, self._ctx, self._borrowed = alphabet, C.c_void_p(ctx), True
+        return self
+
     def close(self):
         if getattr(self, "_ctx", None):
-            capi.lib().lm_ctx_destroy(self._ctx)
+            if not getattr(self, "_borrowed", False):
+                capi.lib().lm_ctx_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -496,6 +509,16 @@ class Pipeline:
                                                    data.strides[0], length, C.byref(h)))
         return self._seq(h)
 
+    def sequence_from_striped_slab(self, data, length, halo, row_offset):
+        """Row slab [row_offset, row_offset + len(data) - halo) of the striped matrix of a
+        `length`-symbol sequence, followed by `halo` rows (lm_seq_from_striped_slab)."""
+        h = C.c_void_p()
+        rows = data.shape[0] - halo
+        self._check(capi.lib().lm_seq_from_striped_slab(self._ctx, self.alphabet, _ptr(data), rows, halo,
+                                                        data.strides[0], length, row_offset, -(-length // LANES),
+                                                        C.byref(h)))
+        return self._seq(h)
+
     def sequence_from_device(self, device_ptr, rows, wrap, length):
         h = C.c_void_p()
         self._check(capi.lib().lm_seq_from_device(self._ctx, self.alphabet, C.c_void_p(device_ptr), rows, wrap,
@@ -513,6 +536,7 @@ class Pipeline:
 
 
 COLWIN_DTYPE = np.dtype([("row", np.uint64), ("score", np.float32), ("valid", np.uint32)])  # == lm_colwin
+HIT_DTYPE = np.dtype([("row", np.uint64), ("position", np.uint64), ("col", np.uint32), ("score", np.float32)])  # == lm_hit
 
 
 def f32_key(x):
@@ -578,3 +602,116 @@ def argmax_merge(parts, row_offsets, first_cell, total_rows, rule=RULE_AVX2):
     if st < 0:
         raise LightmotifError(st)
     return None if st == capi.EMPTY else _hit(best)
+
+
+class Comm:
+    """``lm_comm``: row-sharded fused scans across the GPUs of one box (include/lightmotif_b200.h).
+
+    ``Comm.local(devices)`` drives N GPUs from this process; ``Comm.from_process_group(pli)`` joins
+    one-process-per-GPU ranks (torchrun): the cudaIpc handles of the exchange buffers travel through
+    ``torch.distributed`` once, after that the GPUs talk through peer-mapped HBM only."""
+
+    def __init__(self, handle, alphabet):
+        self._h, self.alphabet = handle, alphabet
+        L = capi.lib()
+        self.world, self.n_local = L.lm_comm_world(handle), L.lm_comm_n_local(handle)
+        self.ranks = [L.lm_comm_rank(handle, i) for i in range(self.n_local)]
+        self.pipelines = [Pipeline._borrow(L.lm_comm_ctx(handle, i), alphabet) for i in range(self.n_local)]
+
+    @classmethod
+    def local(cls, devices, alphabet=DNA, hit_capacity=0):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        st = capi.lib().lm_comm_init(len(devices), devs, hit_capacity, C.byref(h))
+        if st == capi.ERR_UNSUPPORTED:
+            raise UnsupportedBackend("the devices cannot address each other's memory (or no sm_100 device)")
+        if st != capi.OK:
+            raise LightmotifError(st)
+        return cls(h, alphabet)
+
+    @classmethod
+    def from_process_group(cls, pli, group=None, hit_capacity=0):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = np.zeros(capi.COMM_HANDLE_BYTES, dtype=np.uint8)
+        h = C.c_void_p()
+        pli._check(capi.lib().lm_comm_init_rank(pli._ctx, rank, world, hit_capacity, _ptr(mine), C.byref(h)))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(mine)
+        t = t.cuda() if on_gpu else t
+        allh = torch.empty((world, capi.COMM_HANDLE_BYTES), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allh, t.reshape(1, -1), group=group)
+        handles = np.ascontiguousarray(allh.cpu().numpy())
+        st = capi.lib().lm_comm_connect(h, _ptr(handles))
+        if st != capi.OK:
+            msg = capi.lib().lm_comm_last_error(h).decode()
+            capi.lib().lm_comm_destroy(h)
+            raise LightmotifError(st, msg)
+        self = cls(h, pli.alphabet)
+        self.pipelines = [pli]  # the caller's own wrapper (same context)
+        dist.barrier(group)     # every rank has mapped every buffer before anyone writes
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().lm_comm_destroy(self._h)
+            self._h = None
+            for p in self.pipelines:  # contexts owned by the communicator are gone: slabs still alive
+                if getattr(p, "_borrowed", False):  # free their memory without one (lm_seq_free(NULL, .))
+                    p._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st < 0:
+            raise LightmotifError(st, capi.lib().lm_comm_last_error(self._h).decode())
+        return st
+
+    def _slabs(self, handles):
+        return [DeviceSequence(self.pipelines[i], C.c_void_p(handles[i])) for i in range(self.n_local)]
+
+    def sequence_synthetic(self, total_length, wrap, seed=0x5EED):
+        hs = (C.c_void_p * self.n_local)()
+        self._check(capi.lib().lm_comm_seq_synthetic(self._h, self.alphabet, seed, total_length, wrap, hs))
+        return self._slabs(hs)
+
+    def shard_from_striped(self, data, length, wrap):
+        hs = (C.c_void_p * self.n_local)()
+        rows = data.shape[0] - wrap
+        self._check(capi.lib().lm_comm_shard_from_striped(self._h, self.alphabet, _ptr(data), rows, wrap,
+                                                          data.strides[0], length, hs))
+        return self._slabs(hs)
+
+    def _harr(self, slabs):
+        return (C.c_void_p * self.n_local)(*[s._h for s in slabs])
+
+    def score_argmax_launch(self, slabs, pssm, slot=0):
+        p, stride = pad_pssm(pssm, self.alphabet)
+        self._check(capi.lib().lm_comm_score_argmax_f32_launch(self._h, self._harr(slabs), _ptr(p), p.shape[0], stride, slot))
+
+    def score_argmax_finish(self, slot=0, rule=RULE_AVX2):
+        best = Hit()
+        st = self._check(capi.lib().lm_comm_score_argmax_f32_finish(self._h, slot, rule, C.byref(best)))
+        return None if st == capi.EMPTY else _hit(best)
+
+    def score_argmax(self, slabs, pssm, rule=RULE_AVX2):
+        self.score_argmax_launch(slabs, pssm, 0)
+        return self.score_argmax_finish(0, rule)
+
+    def score_threshold(self, slabs, pssm, t, cap=1 << 20, with_counts=False):
+        p, stride = pad_pssm(pssm, self.alphabet)
+        hits = (Hit * cap)()
+        count = C.c_size_t(0)
+        local = (C.c_size_t * self.world)()
+        st = capi.lib().lm_seq_score_threshold_f32_sharded(self._h, self._harr(slabs), _ptr(p), p.shape[0], stride,
+                                                           float(t), hits, cap, C.byref(count), local)
+        if st == capi.ERR_OVERFLOW and count.value > cap:
+            return self.score_threshold(slabs, pssm, t, cap=count.value, with_counts=with_counts)
+        self._check(st)
+        out = [_hit(hits[i]) for i in range(count.value)]
+        return (out, [int(x) for x in local]) if with_counts else out

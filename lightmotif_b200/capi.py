@@ -52,13 +52,18 @@ SYMBOLS = [
     "lm_ctx_last_kernel_ms", "lm_ctx_last_sm_clock_mhz", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
     "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_argmax_u8", "lm_max_u8",
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
-    "lm_seq_from_striped", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
+    "lm_seq_from_striped", "lm_seq_from_striped_slab", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
     "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
     "lm_plan_filter", "lm_plan_filter_protein",
+    "lm_comm_init", "lm_comm_init_rank", "lm_comm_connect", "lm_comm_destroy", "lm_comm_last_error",
+    "lm_comm_world", "lm_comm_n_local", "lm_comm_ctx", "lm_comm_rank", "lm_comm_shard_from_striped",
+    "lm_comm_seq_synthetic", "lm_comm_score_argmax_f32_launch", "lm_comm_score_argmax_f32_finish",
+    "lm_seq_score_argmax_f32_sharded", "lm_seq_score_threshold_f32_sharded",
 ]
+MAX_RANKS, COMM_HANDLE_BYTES = 16, 64
 
 
 def lib():
@@ -113,6 +118,7 @@ def _declare(L):
     L.lm_seq_from_ascii.argtypes = [vp, i, vp, sz, i, sz, C.POINTER(vp), szp]
     L.lm_seq_from_symbols.argtypes = [vp, i, vp, sz, sz, C.POINTER(vp)]
     L.lm_seq_from_striped.argtypes = [vp, i, vp, sz, sz, sz, sz, C.POINTER(vp)]
+    L.lm_seq_from_striped_slab.argtypes = [vp, i, vp, sz, sz, sz, sz, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.lm_seq_from_device.argtypes = [vp, i, vp, sz, sz, sz, C.POINTER(vp)]
     L.lm_seq_synthetic.argtypes = [vp, i, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, sz, C.POINTER(vp)]
     L.lm_seq_configure_wrap.argtypes = [vp, vp, sz]
@@ -137,6 +143,24 @@ def _declare(L):
     L.lm_decode_keys.restype = None
     L.lm_plan_filter.argtypes = [vp, sz, sz, C.c_double, i, C.c_double, i, i, C.POINTER(FilterPlan)]
     L.lm_plan_filter_protein.argtypes = [vp, sz, sz, C.c_double, i, C.c_double, i, C.POINTER(FilterPlan), vp]
+    L.lm_comm_init.argtypes = [i, vp, sz, C.POINTER(vp)]
+    L.lm_comm_init_rank.argtypes = [vp, i, i, sz, vp, C.POINTER(vp)]
+    L.lm_comm_connect.argtypes = [vp, vp]
+    L.lm_comm_destroy.argtypes = [vp]
+    L.lm_comm_destroy.restype = None
+    L.lm_comm_last_error.argtypes = [vp]
+    L.lm_comm_last_error.restype = C.c_char_p
+    L.lm_comm_world.argtypes = [vp]
+    L.lm_comm_n_local.argtypes = [vp]
+    L.lm_comm_ctx.argtypes = [vp, i]
+    L.lm_comm_ctx.restype = vp
+    L.lm_comm_rank.argtypes = [vp, i]
+    L.lm_comm_shard_from_striped.argtypes = [vp, i, vp, sz, sz, sz, sz, C.POINTER(vp)]
+    L.lm_comm_seq_synthetic.argtypes = [vp, i, C.c_uint64, C.c_uint64, sz, C.POINTER(vp)]
+    L.lm_comm_score_argmax_f32_launch.argtypes = [vp, C.POINTER(vp), vp, sz, sz, i]
+    L.lm_comm_score_argmax_f32_finish.argtypes = [vp, i, i, hitp]
+    L.lm_seq_score_argmax_f32_sharded.argtypes = [vp, C.POINTER(vp), vp, sz, sz, i, hitp]
+    L.lm_seq_score_threshold_f32_sharded.argtypes = [vp, C.POINTER(vp), vp, sz, sz, C.c_float, hitp, sz, szp, szp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("lm_abi_version",):

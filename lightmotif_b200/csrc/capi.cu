@@ -2,6 +2,7 @@
 // device-resident sequence handles, host<->device plumbing and the tiny host
 // finishing steps (tie rules over 32 per-column winners, hit ordering).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -10,97 +11,29 @@
 #include <thread>
 #include <vector>
 
-#include "common.cuh"
+#include "internal.cuh"
 #include "prune.cuh"
 #include "reduce.cuh"
 #include "score.cuh"
 #include "seqops.cuh"
 
 using namespace lm;
-
-// ------------------------------------------------------------------ context
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-};
-
-struct lm_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool timed = false;
-  float last_ms = 0.f;
-  uint64_t launches = 0;
-  char err[256] = {0};
-  DevBuf d_in, d_out, d_table, d_table2, d_small, d_hits;  // device scratch, grown on demand
-  // protein filter: class-coded copy of the last sequence scanned (one-entry cache keyed by the
-  // sequence buffer and the residue -> class map)
-  DevBuf d_class;
-  const uint8_t* class_src = nullptr;
-  size_t class_rows = 0;
-  uint8_t class_lut[32] = {0};
-  std::vector<uint8_t> pplan_key;
-  ProteinPlan pplan_cache;
-  int opt_prune = 1;                      // LM_OPT_PRUNE: 0 never, 1 auto, 2 whenever a plan exists
-  int opt_filter_rows = 0;                // LM_OPT_FILTER_ROWS: 0 = planner decides
-  int opt_filter_mode = 0;                // LM_OPT_FILTER_MODE: 0 = planner decides, 1 = single rows, 2 = paired rows
-  int opt_class_cache = 1;                // LM_OPT_CLASS_CACHE: reuse the class-coded copy of a protein sequence
-  int opt_reserve_sms = 0;                // LM_OPT_RESERVE_SMS: SMs left free for concurrent (NCCL) kernels
-  size_t opt_boot_rows = 262144;          // LM_OPT_BOOT_ROWS: rows scored exactly first to seed the running maximum
-  uint64_t stats[4] = {0, 0, 0, 0};       // last scoring call: candidates, overflow tiles, pruned?, filter rows
-  float sm_mhz = 0.f;                     // SM clock the last filtered scan ran at (cycle counter / global timer)
-  // the last matrix uploaded to d_table / d_table2 and the last filter plan: a
-  // caller scanning many sequences (or benchmarking) with one PSSM pays for the
-  // host-side set-up once
-  std::vector<uint8_t> table_key, table8_key, plan_key;
-  PrunePlan plan_cache;
-  // in-flight fused argmax calls (launch / finish split, LM_SLOTS slots): result blocks
-  // live at d_small + slot * 1024 and are copied to pinned host memory
-  struct Slot {
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
-    void* h = nullptr;  // pinned SmallBlock
-    int state = 0;      // 0 idle, 1 in flight, 2 in flight but empty (LM_EMPTY)
-    size_t n_rows = 0;
-    bool pruned = false;
-    int r = 0;
-  } slots[LM_SLOTS];
-  void* h_pin = nullptr;                          // pinned host staging
-  size_t h_pin_bytes = 0;
-};
-
-struct lm_seq {
-  int alphabet = 0;
-  int device = 0;
-  uint8_t* data = nullptr;  // [alloc_rows][32]
-  bool owned = true;
-  size_t rows = 0, wrap = 0, length = 0, alloc_rows = 0;
-};
+using namespace lmi;
 
 namespace {
-
 constexpr size_t SLACK_ROWS = 64;      // readable rows kept behind rows + wrap
 constexpr size_t SMALL_BYTES = 1 << 20;  // keys / counters block
+// d_small: launch slot s owns [s * 1024, s * 1024 + 512); the synchronous calls use the block below
+constexpr size_t SYNC_SMALL_OFF = (size_t)LM_SLOTS * 1024;
+}  // namespace
+
+namespace lmi {
 
 int fail(lm_ctx* ctx, cudaError_t e, const char* what) {
   if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
   cudaGetLastError();  // clear sticky-free errors
   return e == cudaErrorMemoryAllocation ? LM_ERR_OOM : LM_ERR_CUDA;
 }
-
-#define LM_TRY(expr)                                      \
-  do {                                                    \
-    cudaError_t _e = (expr);                              \
-    if (_e != cudaSuccess) return fail(ctx, _e, #expr);   \
-  } while (0)
-
-#define LM_CHECK(expr)          \
-  do {                          \
-    int _s = (expr);            \
-    if (_s < 0) return _s;      \
-  } while (0)
 
 int ensure(lm_ctx* ctx, DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return LM_OK;
@@ -157,11 +90,6 @@ void build_table_u8(int alphabet, const uint8_t* dm, size_t m, size_t stride, ui
   for (size_t j = 0; j < m; ++j)
     for (int s = 0; s < k; ++s) dst[j * kp + s] = dm[j * stride + s];
 }
-
-struct ColKeys {
-  unsigned long long keys[32];
-  uint32_t first_cell;
-};
 
 void decode_colwins(const unsigned long long* keys, bool is_u8, lm_colwin* out) {
   for (int c = 0; c < 32; ++c) {
@@ -315,7 +243,7 @@ int run_score(lm_ctx* ctx, int alphabet, bool is_u8, int mode, const uint8_t* se
 int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
   std::vector<uint8_t> key = matrix_key(3, LM_DNA, pssm, m, stride, 4);
   if (key == ctx->table8_key && ctx->d_table2.p) return LM_OK;
-  ctx->table8_key = key;
+  ctx->table8_key.clear();  // set again only once the new table is on the device
   const size_t m_pad = (m + 3) & ~(size_t)3;  // rows >= m are +0.0 (the recheck loop is unrolled by 4)
   const size_t bytes = m_pad * 8 * 4;
   LM_CHECK(ensure_pinned(ctx, bytes));
@@ -326,6 +254,7 @@ int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
     for (int a = 0; a < 8; ++a) h[j * 8 + a] = a < 5 ? pssm[j * stride + a] : 0.f;
   LM_TRY(cudaMemcpyAsync(ctx->d_table2.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->table8_key.swap(key);
   return LM_OK;
 }
 
@@ -364,7 +293,7 @@ ProteinPlan cached_protein_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t
 int upload_table32(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
   std::vector<uint8_t> key = matrix_key(8, LM_PROTEIN, pssm, m, stride, 4);
   if (key == ctx->table8_key && ctx->d_table2.p) return LM_OK;
-  ctx->table8_key = key;
+  ctx->table8_key.clear();
   const size_t m_pad = (m + 3) & ~(size_t)3;
   const size_t bytes = m_pad * 32 * 4;
   LM_CHECK(ensure_pinned(ctx, bytes));
@@ -375,26 +304,27 @@ int upload_table32(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
     for (int a = 0; a < 21; ++a) h[j * 32 + a] = pssm[j * stride + a];
   LM_TRY(cudaMemcpyAsync(ctx->d_table2.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->table8_key.swap(key);
   return LM_OK;
 }
 
 int ensure_class_copy(lm_ctx* ctx, const lm_seq* seq, const uint8_t* class_of) {
-  if (ctx->opt_class_cache && seq->owned && ctx->class_src == seq->data && ctx->class_rows == seq->alloc_rows && ctx->d_class.p &&
-      std::memcmp(ctx->class_lut, class_of, 32) == 0)
-    return LM_OK;  // same (library-owned, hence unmodified) sequence, same classes: the copy is still valid
+  if (ctx->opt_class_cache && seq->owned && ctx->class_seq_id == seq->id && ctx->class_rows == seq->alloc_rows &&
+      ctx->d_class.p && std::memcmp(ctx->class_lut, class_of, 32) == 0)
+    return LM_OK;  // same handle (ids are never reused), same rows, same classes: the copy is still valid
   LM_CHECK(ensure(ctx, ctx->d_class, seq->alloc_rows * 32));
   LM_TRY(launch_classmap(seq->data, seq->alloc_rows * 32, (uint8_t*)ctx->d_class.p, class_of, ctx->sm_count,
                          ctx->stream));
   ctx->launches += 1;
-  ctx->class_src = seq->data;
+  ctx->class_seq_id = seq->id;
   ctx->class_rows = seq->alloc_rows;
   std::memcpy(ctx->class_lut, class_of, 32);
   return LM_OK;
 }
 
-int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
+int fetch_stats(lm_ctx* ctx, const PrunePlan& plan, size_t small_off = 0) {
   unsigned long long st[2] = {0, 0};
-  LM_TRY(cudaMemcpyAsync(st, (uint8_t*)ctx->d_small.p + 272, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(st, (uint8_t*)ctx->d_small.p + small_off + 272, 16, cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->stats[0] = st[0];
   ctx->stats[1] = st[1];
@@ -402,14 +332,6 @@ int fetch_stats(lm_ctx* ctx, const PrunePlan& plan) {
   ctx->stats[3] = (uint64_t)plan.r | ((uint64_t)plan.pair << 8);
   return LM_OK;
 }
-
-// small block layout: [0,256) column keys, [256] first cell, [264] hit count, [272..296) filter stats
-struct SmallBlock {
-  ColKeys ck;                    // 260 bytes (+4 pad)
-  unsigned long long count;      // @264
-  unsigned long long stats[5];   // @272: candidates, overflow tiles, tile counter, SM cycles, ns (CTA 0's producer)
-};
-static_assert(offsetof(SmallBlock, count) == 264 && offsetof(SmallBlock, stats) == 272, "small block layout");
 
 int fetch_colkeys(lm_ctx* ctx, ColKeys* out, const PrunePlan* plan = nullptr) {
   SmallBlock sb;
@@ -434,6 +356,9 @@ int seq_alloc(lm_ctx* ctx, int alphabet, size_t rows, size_t wrap, size_t length
   s->wrap = wrap;
   s->length = length;
   s->alloc_rows = rows + wrap + SLACK_ROWS;
+  s->rows_global = rows;
+  static std::atomic<uint64_t> next_id{1};
+  s->id = next_id.fetch_add(1);
   // stream-ordered allocation from the device's default pool (kept warm: see lm_ctx_create): a caller
   // that uploads, scans and frees sequence after sequence does not pay the OS for every cycle
   cudaError_t e = cudaMallocAsync((void**)&s->data, s->alloc_rows * 32, ctx->stream);
@@ -775,9 +700,9 @@ int lm_max_u8(lm_ctx* ctx, const uint8_t* scores, size_t rows, size_t stride, ui
   return s;
 }
 
-static int fetch_hits(lm_ctx* ctx, lm_hit* hits, size_t cap, size_t* count) {
+static int fetch_hits(lm_ctx* ctx, lm_hit* hits, size_t cap, size_t* count, size_t small_off = 0) {
   unsigned long long total = 0;
-  LM_TRY(cudaMemcpyAsync(&total, (uint8_t*)ctx->d_small.p + 264, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  LM_TRY(cudaMemcpyAsync(&total, (uint8_t*)ctx->d_small.p + small_off + 264, 8, cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   size_t n = (size_t)std::min<unsigned long long>(total, cap);
   if (n) {
@@ -890,6 +815,16 @@ int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t r
   return LM_OK;
 }
 
+int lm_seq_from_striped_slab(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t rows, size_t halo, size_t stride,
+                             size_t length, uint64_t row_offset, uint64_t rows_global, lm_seq** out) {
+  if (row_offset + rows > rows_global || (uint64_t)(length + 31) / 32 != rows_global) return LM_ERR_INVALID_ARG;
+  int st = lm_seq_from_striped(ctx, alphabet, data, rows, halo, stride, length, out);
+  if (st < 0) return st;
+  (*out)->row_offset = row_offset;
+  (*out)->rows_global = rows_global;
+  return LM_OK;
+}
+
 int lm_seq_from_device(lm_ctx* ctx, int alphabet, void* device_ptr, size_t rows, size_t wrap,
                        size_t length, lm_seq** out) {
   LM_CHECK(bind(ctx));
@@ -920,6 +855,8 @@ int lm_seq_synthetic(lm_ctx* ctx, int alphabet, uint64_t seed, uint64_t total_le
   if (rows_global + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
   lm_seq* s = nullptr;
   LM_CHECK(seq_alloc(ctx, alphabet, n_rows, wrap, total_length, &s));
+  s->row_offset = row_begin;
+  s->rows_global = rows_global;
   timer_begin(ctx);
   cudaError_t e = launch_synth(s->data, s->alloc_rows, rows_global, row_begin, total_length, seed, alphabet,
                                ctx->sm_count, ctx->stream);
@@ -936,6 +873,9 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
   if (!seq) return LM_ERR_INVALID_ARG;
   if (wrap <= seq->wrap) return LM_OK;  // seq.rs:370: only grows
   if (!seq->owned) return LM_ERR_UNSUPPORTED;
+  // a row slab's halo rows are the NEXT rows of the global matrix, which this handle does not hold:
+  // the local closed form would overwrite them with wrong symbols
+  if (seq->is_slab() || seq->length > seq->rows * 32) return LM_ERR_UNSUPPORTED;
   if (seq->rows + wrap >= (1ull << 32)) return LM_ERR_UNSUPPORTED;
   if (seq->rows + wrap + SLACK_ROWS > seq->alloc_rows) {
     size_t new_alloc = seq->rows + wrap + SLACK_ROWS;
@@ -946,7 +886,6 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
                                               (new_alloc - seq->rows - seq->wrap) * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFreeAsync(nd, ctx->stream); return fail(ctx, e, "grow sequence"); }
-    if (ctx->class_src == seq->data) ctx->class_src = nullptr;
     cudaFreeAsync(seq->data, ctx->stream);
     seq->data = nd;
     seq->alloc_rows = new_alloc;
@@ -961,7 +900,7 @@ int lm_seq_configure_wrap(lm_ctx* ctx, lm_seq* seq, size_t wrap) {
   }
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   seq->wrap = wrap;
-  if (ctx->class_src == seq->data) ctx->class_src = nullptr;  // wrap rows changed
+  if (ctx->class_seq_id == seq->id) ctx->class_seq_id = 0;  // wrap rows changed
   return LM_OK;
 }
 
@@ -992,7 +931,7 @@ void lm_seq_free(lm_ctx* ctx, lm_seq* seq) {
   if (ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->class_src == seq->data) ctx->class_src = nullptr;  // the class-coded copy dies with its sequence
+    if (ctx->class_seq_id == seq->id) ctx->class_seq_id = 0;  // the class-coded copy dies with its sequence
   }
   if (seq->owned && seq->data) {
     if (ctx) cudaFreeAsync(seq->data, ctx->stream);
@@ -1044,8 +983,12 @@ int lm_seq_score_u8(lm_ctx* ctx, const lm_seq* seq, const uint8_t* dm, size_t m,
   return seq_score(ctx, seq, true, dm, m, dm_stride, row_begin, row_end, out, out_stride, out_is_device, out_rows);
 }
 
-int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m,
-                                   size_t pssm_stride, size_t row_begin, size_t row_end, int slot) {
+}  // extern "C"
+
+namespace lmi {
+
+int argmax_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride, size_t row_begin,
+                  size_t row_end, int slot, const PeerLink* link) {
   LM_CHECK(bind(ctx));
   if (!seq || !pssm || slot < 0 || slot >= LM_SLOTS || pssm_stride < (size_t)alphabet_k(seq->alphabet))
     return LM_ERR_INVALID_ARG;
@@ -1054,7 +997,18 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
   if (sl.state != 0) return LM_ERR_INVALID_ARG;  // previous launch on this slot not finished
   int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
   if (st < 0) return st;
-  if (st == LM_EMPTY) { sl.state = 2; return LM_OK; }
+  const size_t off = (size_t)slot * 1024;
+  uint8_t* small = (uint8_t*)ctx->d_small.p + off;
+  const bool linked = link && link->world > 1;
+  if (st == LM_EMPTY) {
+    sl.state = 2;
+    if (linked) {  // the other ranks still wait for this rank's (empty) block
+      LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+      LM_TRY(launch_publish(*link, (const unsigned long long*)small, ctx->stream));
+      ctx->launches += 1;
+    }
+    return LM_OK;
+  }
   LM_CHECK(limits_ok(seq->alphabet, m));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
   const size_t n_rows = row_end - row_begin;
@@ -1062,7 +1016,8 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
   ProteinPlan pplan;
   const bool protein = seq->alphabet == LM_PROTEIN;
   if (ctx->opt_prune && n_rows > 2 * ctx->opt_boot_rows) {
-    const double npos = (double)n_rows * 32.0;
+    // a row-sharded scan is planned for the whole matrix: every rank filters at the global maximum
+    const double npos = (double)(linked && seq->rows_global ? seq->rows_global : n_rows) * 32.0;
     if (protein) {
       pplan = cached_protein_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
       plan = pplan.plan;
@@ -1072,8 +1027,6 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
   if (plan.ok) LM_CHECK(protein ? upload_table32(ctx, pssm, m, pssm_stride) : upload_table8(ctx, pssm, m, pssm_stride));
-  const size_t off = (size_t)slot * 1024;
-  uint8_t* small = (uint8_t*)ctx->d_small.p + off;
   LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
   LM_TRY(cudaEventRecord(sl.ev0, ctx->stream));
   if (plan.ok) {
@@ -1099,11 +1052,16 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
     pa.plan = plan;
     pa.colkeys = (unsigned long long*)small;
     pa.stats = (unsigned long long*)(small + 272);
+    if (linked) pa.link = *link;  // the scan kernel itself shares the maximum and publishes the block
     LM_TRY(launch_prune(false, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
     ctx->launches += 1;
   } else {
     LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_ARGMAX, seq->data, seq->alloc_rows, m, row_begin, row_end,
                        nullptr, 0, 0.f, 0, nullptr, 0, false, off));
+    if (linked) {
+      LM_TRY(launch_publish(*link, (const unsigned long long*)small, ctx->stream));
+      ctx->launches += 1;
+    }
   }
   LM_TRY(cudaEventRecord(sl.ev1, ctx->stream));
   LM_TRY(cudaMemcpyAsync(sl.h, small, sizeof(SmallBlock), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1113,6 +1071,15 @@ int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* 
   sl.pruned = plan.ok;
   sl.r = plan.r | (plan.pair << 8);
   return LM_OK;
+}
+
+}  // namespace lmi
+
+extern "C" {
+
+int lm_seq_score_argmax_f32_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m,
+                                   size_t pssm_stride, size_t row_begin, size_t row_end, int slot) {
+  return argmax_launch(ctx, seq, pssm, m, pssm_stride, row_begin, row_end, slot, nullptr);
 }
 
 int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best, lm_colwin* per_column,
@@ -1160,21 +1127,19 @@ int lm_seq_score_argmax_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, s
   return lm_seq_score_argmax_f32_finish(ctx, 0, rule, best, per_column, first_cell);
 }
 
-int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
-                               size_t row_begin, size_t row_end, float t, lm_hit* hits, size_t cap, size_t* count) {
-  LM_CHECK(bind(ctx));
-  if (count) *count = 0;
-  if (!seq || !pssm || (cap && !hits) || pssm_stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
-  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
-  int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
-  if (st == LM_EMPTY) return LM_OK;
-  if (st < 0) return st;
+}  // extern "C"
+
+namespace lmi {
+
+int threshold_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride, size_t row_begin,
+                     size_t row_end, float t, lm_hit* d_hits, size_t cap, size_t small_off, const PeerLink* link,
+                     PrunePlan* plan_out) {
   LM_CHECK(limits_ok(seq->alphabet, m));
-  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
   LM_CHECK(upload_table(ctx, seq->alphabet, pssm, m, pssm_stride, false));
   PrunePlan plan;
   ProteinPlan pplan;
   const bool protein = seq->alphabet == LM_PROTEIN;
+  const bool linked = link && link->world > 1;
   if (ctx->opt_prune && row_end - row_begin > 4096) {
     const double npos = (double)(row_end - row_begin) * 32.0;
     if (protein) {
@@ -1185,10 +1150,16 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
     }
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
+  if (plan_out) *plan_out = plan;
+  // a slab reports its hits in the coordinates of the whole matrix
+  const uint64_t row_add = seq->is_slab() ? seq->row_offset + row_begin : 0;
+  const uint64_t pos_rows = seq->is_slab() ? seq->rows_global : 0;
+  uint8_t* small = (uint8_t*)ctx->d_small.p + small_off;
+  LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
+  ctx->stats[0] = ctx->stats[1] = ctx->stats[2] = ctx->stats[3] = 0;
+  timer_begin(ctx);
   if (plan.ok) {
     LM_CHECK(protein ? upload_table32(ctx, pssm, m, pssm_stride) : upload_table8(ctx, pssm, m, pssm_stride));
-    uint8_t* small = (uint8_t*)ctx->d_small.p;
-    LM_TRY(cudaMemsetAsync(small, 0, 512, ctx->stream));
     PruneArgs pa;
     pa.seq = seq->data;
     if (protein) {
@@ -1206,20 +1177,64 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
     pa.table = (const float*)ctx->d_table2.p;
     pa.plan = plan;
     pa.thr = t;
-    pa.hits = (lm_hit*)ctx->d_hits.p;
+    pa.hits = d_hits;
     pa.cap = cap;
+    pa.colkeys = (unsigned long long*)small;
     pa.count = (unsigned long long*)(small + 264);
     pa.stats = (unsigned long long*)(small + 272);
-    timer_begin(ctx);
+    pa.row_add = row_add;
+    pa.pos_rows = pos_rows;
+    if (linked) pa.link = *link;
     LM_TRY(launch_prune(true, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
-    timer_end(ctx);
-    ctx->launches += 1;
-    LM_CHECK(fetch_stats(ctx, plan));
   } else {
-    LM_CHECK(run_score(ctx, seq->alphabet, false, MODE_THRESHOLD, seq->data, seq->alloc_rows, m, row_begin, row_end,
-                       nullptr, 0, t, 0, (lm_hit*)ctx->d_hits.p, cap));
+    ScoreArgs a;
+    a.seq = seq->data;
+    a.avail_rows = seq->alloc_rows;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
+    a.pad_sym = pad_symbol(seq->alphabet);
+    a.tables = (const uint32_t*)ctx->d_table.p;
+    a.m_pad = table_mpad(m);
+    a.n_motifs = 1;
+    a.colkeys = (unsigned long long*)small;
+    a.first_cell = (uint32_t*)(small + 256);
+    a.count = (unsigned long long*)(small + 264);
+    std::memcpy(&a.thr_bits, &t, 4);
+    a.hits = d_hits;
+    a.cap = cap;
+    a.row_add = row_add;
+    a.pos_rows = pos_rows;
+    LM_TRY(launch_score(seq->alphabet, MODE_THRESHOLD, false, a, std::max(1, ctx->sm_count - ctx->opt_reserve_sms),
+                        ctx->stream));
+    if (linked) {
+      LM_TRY(launch_publish(*link, (const unsigned long long*)small, ctx->stream));
+      ctx->launches += 1;
+    }
   }
-  return fetch_hits(ctx, hits, cap, count);
+  timer_end(ctx);
+  ctx->launches += 1;
+  return LM_OK;
+}
+
+}  // namespace lmi
+
+extern "C" {
+
+int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride,
+                               size_t row_begin, size_t row_end, float t, lm_hit* hits, size_t cap, size_t* count) {
+  LM_CHECK(bind(ctx));
+  if (count) *count = 0;
+  if (!seq || !pssm || (cap && !hits) || pssm_stride < (size_t)alphabet_k(seq->alphabet)) return LM_ERR_INVALID_ARG;
+  if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
+  int st = check_score_args(m, seq->rows, seq->wrap, seq->length, row_begin, row_end);
+  if (st == LM_EMPTY) return LM_OK;
+  if (st < 0) return st;
+  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(cap, 1) * sizeof(lm_hit)));
+  PrunePlan plan;
+  LM_CHECK(threshold_launch(ctx, seq, pssm, m, pssm_stride, row_begin, row_end, t, (lm_hit*)ctx->d_hits.p, cap,
+                            SYNC_SMALL_OFF, nullptr, &plan));
+  if (plan.ok) LM_CHECK(fetch_stats(ctx, plan, SYNC_SMALL_OFF));
+  return fetch_hits(ctx, hits, cap, count, SYNC_SMALL_OFF);
 }
 
 // ---- many motifs over one resident sequence (the lightmotif-cli job loop).  Every motif is

@@ -34,7 +34,63 @@ __host__ __device__ inline float key_to_f32(uint32_t k) {
 #endif
 }
 
+// ---- coupling of one rank's fused scan to the other ranks of a row-sharded scan (comm.cu) -------
+// Every rank owns an exchange buffer in its HBM that all ranks map (peer access within a process,
+// cudaIpc between processes).  During a scan the ranks share their running maximum through a
+// tagged word per launch slot ("floor": epoch << 32 | score key, raised with system-scope atomicMax
+// over NVLink), so every GPU filters at the GLOBAL maximum found so far; when a rank's scan ends,
+// the last warp of its scan kernel writes the rank's result block into every rank's buffer and
+// raises an arrival flag there (release at system scope).  No collective kernel is involved.
+constexpr int XBLOCK_WORDS = 40;  // u64 words of a published result block (320 bytes)
+// words: [0,32) per-column winner keys, [32] first cell (f32 bits), [33] hit count (threshold scans),
+//        [34] first global row of the rank's slab, [35] rows of the slab, [36] epoch, [37] candidates,
+//        [38] overflow tiles
+struct PeerLink {
+  int world = 0, rank = 0;
+  uint32_t epoch = 0;                                  // same on all ranks for one sharded scan
+  unsigned long long* floor_local = nullptr;           // this rank's floor word of the slot
+  unsigned long long* const* floor_peers = nullptr;    // device array [world]: that word on every rank
+  unsigned long long* const* gather_peers = nullptr;   // device array [world]: where THIS rank's block goes on every rank
+  unsigned long long* const* flag_peers = nullptr;     // device array [world]: the arrival flag to raise there
+  uint64_t row_offset = 0, n_rows = 0;
+};
+
 #ifdef __CUDACC__
+// score key of the shared floor if it belongs to this scan, else 0
+__device__ __forceinline__ uint32_t peer_floor_key(const PeerLink& l) {
+  const unsigned long long v = __ldcg(l.floor_local);
+  return (uint32_t)(v >> 32) == l.epoch ? (uint32_t)v : 0u;
+}
+// raise the floor on every rank (called by a whole warp; lane p serves rank p, p + 32, ...)
+__device__ __forceinline__ void peer_push_floor(const PeerLink& l, uint32_t key, int lane) {
+  const unsigned long long v = ((unsigned long long)l.epoch << 32) | key;
+  for (int p = lane; p < l.world; p += 32) atomicMax_system(l.floor_peers[p], v);
+}
+// publish this rank's result block (`small` = SmallBlock in local HBM) to every rank; one warp.
+// All earlier writes to `small` by this grid must be visible to the calling warp.
+__device__ __forceinline__ void peer_publish(const PeerLink& l, const unsigned long long* small, int lane) {
+  unsigned long long w0 = __ldcg(&small[lane]);   // keys
+  unsigned long long w1 = 0;                      // words 32..39
+  if (lane == 0) w1 = __ldcg(&small[32]) & 0xffffffffull;  // first cell
+  else if (lane == 1) w1 = __ldcg(&small[33]);             // hit count
+  else if (lane == 2) w1 = l.row_offset;
+  else if (lane == 3) w1 = l.n_rows;
+  else if (lane == 4) w1 = l.epoch;
+  else if (lane == 5) w1 = __ldcg(&small[34]);             // candidates
+  else if (lane == 6) w1 = __ldcg(&small[35]);             // overflow tiles
+  for (int p = 0; p < l.world; ++p) {
+    volatile unsigned long long* dst = l.gather_peers[p];
+    dst[lane] = w0;
+    if (lane < XBLOCK_WORDS - 32) dst[32 + lane] = w1;
+  }
+  __threadfence_system();
+  __syncwarp();
+  for (int p = lane; p < l.world; p += 32) {
+    unsigned long long* f = l.flag_peers[p];
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)l.epoch) : "memory");
+  }
+}
+
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -85,6 +141,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+// wait with a suspend-time hint: the warp is parked by the hardware for up to `hint_ns` per attempt
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITH_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONEH_%=;\n"
+      "bra WAITH_%=;\n"
+      "DONEH_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(hint_ns)
+      : "memory");
+}
+// L2 prefetch of a contiguous global range (bytes % 16 == 0, 16-byte aligned): no shared-memory
+// destination, so the bytes in flight are not limited by the tile ring
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,

@@ -33,6 +33,7 @@
 //   fp32score(p) >= T  ==>  sum_q(p) >= ceil((T - eps - c0) / delta)  (- 1 safety)
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -59,6 +60,18 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #ifndef LM_PRUNE_EXP
 #define LM_PRUNE_EXP 0
 #endif
+#ifndef LM_PRUNE_L2PF
+#define LM_PRUNE_L2PF 0      // L2 prefetch distance in grid rounds (0 = off): tile t + L2PF * gridDim.x
+#endif
+#ifndef LM_PRUNE_PRODRECHECK
+#define LM_PRUNE_PRODRECHECK 0  // 1: the producer warp rechecks the queued candidates (before it reloads the stage)
+#endif
+#ifndef LM_PRUNE_PROF
+#define LM_PRUNE_PROF 0      // 1: CTAs 0 and 77 print a cycle breakdown of their pipeline (diagnostic builds only)
+#endif
+#ifndef LM_PRUNE_WAIT
+#define LM_PRUNE_WAIT 0      // 0: try_wait + nanosleep back-off, 1: plain try_wait loop, 2: try_wait with suspend hint
+#endif
 #ifndef LM_PRUNE_NSTAGE
 #define LM_PRUNE_NSTAGE 2
 #endif
@@ -73,6 +86,18 @@ constexpr int PL = LM_PRUNE_PL;        // rows per thread per tile (odd => confl
 constexpr int WARP_ROWS = 4 * PL;
 constexpr int PTILE_ROWS = PW * WARP_ROWS;
 constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
+
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
+#if LM_PRUNE_WAIT == 1
+  (void)ns;
+  mbar_wait(bar, parity);
+#elif LM_PRUNE_WAIT == 2
+  (void)ns;
+  mbar_wait_hint(bar, parity, 20000u);
+#else
+  mbar_wait_backoff(bar, parity, ns);
+#endif
+}
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
 struct PSmem {
@@ -81,7 +106,9 @@ struct PSmem {
 // pipeline control block: full[s] (TMA landed + descriptor valid) / empty[s] (all consumer warps done)
 struct Ctl {
   uint64_t full[NSTAGE], empty[NSTAGE];
-  struct { unsigned long long tile; uint32_t bias4; float thr; } desc[NSTAGE];
+  struct { unsigned long long tile; uint32_t bias4; float thr; uint32_t avail, valid; } desc[NSTAGE];  // avail: rows the copy delivers; valid: rows of the tile inside the scored range
+  uint32_t nq[NSTAGE][PW];  // candidate-queue lengths of the tile in each stage, per consumer warp
+  long long t_issue[NSTAGE];  // LM_PRUNE_PROF: SM clock when the stage's TMA copy was issued
 };
 __host__ __device__ inline PSmem psmem(int m, int tab_stride) {
   PSmem s;
@@ -89,7 +116,7 @@ __host__ __device__ inline PSmem psmem(int m, int tab_stride) {
   s.table_off = 0;
   s.ctl_off = ((uint32_t)((m + 3) & ~3) * tab_stride * 4 + 127) & ~127u;
   s.queue_off = (s.ctl_off + (uint32_t)sizeof(Ctl) + 127) & ~127u;
-  s.raw_off = s.queue_off + PW * QCAP * 4;
+  s.raw_off = s.queue_off + NSTAGE * PW * QCAP * 4;
   s.raw_bytes = (tt * 32 + 127) & ~127u;
   s.total = s.raw_off + NSTAGE * s.raw_bytes;
   return s;
@@ -134,9 +161,9 @@ __device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel
     unsigned long long slot = atomicAdd(a.count, 1ull);
     if (slot < a.cap) {
       lm_hit h;
-      h.row = rel_row;
+      h.row = rel_row + a.row_add;
       h.col = col;
-      h.position = (uint64_t)col * (a.row_end - a.row_begin) + rel_row;
+      h.position = (uint64_t)col * (a.pos_rows ? a.pos_rows : a.row_end - a.row_begin) + h.row;
       h.score = s;
       a.hits[slot] = h;
     }
@@ -203,7 +230,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     // ===================== producer warp: claims tiles, stages them with bulk TMA, publishes the
     // threshold each tile is to be filtered at.  Tiles are claimed one at a time from a global
     // counter, so the CTAs of the whole grid sweep the sequence as one dense window.
-    uint32_t thr_key = 0xffffffffu, bias4 = 0;
+    uint32_t thr_key = 0xffffffffu, bias4 = 0, pushed_key = 0;
     float thr = THR ? a.thr : -INFINITY;
     // CTA 0 measures the SM clock the scan runs at: cycle counter vs global nanosecond timer
     long long clk0 = 0;
@@ -212,19 +239,91 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       clk0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
     }
-    for (uint32_t it = 0;; ++it) {
+    // Exact recheck of the candidates the consumer warps queued for the tile in stage s (sequential
+    // f32 sum in the reference's order, from the tile still in shared memory).  It runs HERE, on the
+    // otherwise idle producer warp, between "all consumers are done with the stage" and its reload:
+    // the filter warps never leave their uniform fast path for it, so they stay in step with each
+    // other and the 2-deep tile ring does not stall on the one warp that found a candidate.
+    unsigned long long n_cand = 0;
+    uint32_t* const queues = reinterpret_cast<uint32_t*>(smem + S.queue_off);
+    auto drain = [&](int s) {
+      uint32_t cnt = lane < PW ? ctl->nq[s][lane] : 0u;
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < PW; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      uint32_t ends[PW];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) ends[j] = __shfl_sync(0xffffffffu, incl, j);
+      const uint32_t total = ends[PW - 1];
+      if (total == 0) return;
+      n_cand += total;
+      const uint64_t tile = ctl->desc[s].tile;
+      const float dthr = ctl->desc[s].thr;
+      const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;
+      const uint64_t left = a.row_end - tile_row0;
+      const uint32_t tile_valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
+      const uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
+      for (uint32_t g = lane; g < total * 8; g += 32) {
+        const uint32_t e = g >> 3, b = g & 7;
+        uint32_t w = 0, first = 0;  // queue (= consumer warp) holding entry e, and its first entry
+#pragma unroll
+        for (int j = 0; j < PW - 1; ++j)
+          if (e >= ends[j]) { w = j + 1; first = ends[j]; }
+        const uint32_t code = queues[((uint32_t)s * PW + w) * QCAP + (e - first)];
+        if (!((code >> b) & 1u)) continue;
+        const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
+        if (row >= tile_valid) continue;
+        const float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
+                                     : exact_score(rawb, tab, m_pad, row, col);
+        if (sc >= dthr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
+      }
+      __syncwarp();
+    };
+#if LM_PRUNE_PROF
+    long long p_wait = 0, p_drain = 0, p_issue = 0, p_claim = 0;
+#endif
+    uint32_t it = 0;
+    for (;; ++it) {
       const int s = it % NSTAGE;
+#if LM_PRUNE_PROF
+      const long long p00 = clock64();
+#endif
       // claim the tile and fetch the running maximum first: both round trips overlap the wait
       unsigned long long tile = 0;
       if (lane == 0) tile = atomicAdd(&a.stats[2], 1ull);
       uint32_t sk = 0;
-      if (!THR) sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
-      tile = __shfl_sync(0xffffffffu, tile, 0);
       if (!THR) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
+        sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
+        // row-sharded scan: the maximum the OTHER GPUs have found so far (pushed over NVLink)
+        if (a.link.world > 1 && lane == 0) sk = max(sk, peer_floor_key(a.link));
       }
-      if (it >= NSTAGE) mbar_wait_backoff(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+#if LM_PRUNE_L2PF > 0
+      // the tile some CTA will claim L2PF grid rounds from now: start its trip from HBM to L2 already
+      if (lane == 0) {
+        const unsigned long long pt = tile + (unsigned long long)LM_PRUNE_L2PF * gridDim.x;
+        if (pt < num_tiles) {
+          const uint64_t pr0 = a.row_first + pt * PTILE_ROWS;
+          if (pr0 + PTILE_ROWS <= a.avail_rows) l2_prefetch_bulk(a.seq + pr0 * 32, PTILE_ROWS * 32);
+        }
+      }
+#endif
+      if (!THR) {
+        uint32_t own = lane == 0 && a.link.world > 1 ? (uint32_t)(__ldcg(&a.colkeys[0]) >> 32) : sk;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
+          own = max(own, __shfl_xor_sync(0xffffffffu, own, o));
+        }
+        // CTA 0 tells the other GPUs whenever this GPU's own maximum has risen above the shared one
+        if (a.link.world > 1 && blockIdx.x == 0 && own > pushed_key) {
+          if (own > peer_floor_key(a.link) || pushed_key == 0) peer_push_floor(a.link, own, lane);
+          pushed_key = own;
+        }
+      }
       // ---- current threshold -> byte bias (recomputed only when the threshold moved)
       if (THR ? it == 0 : sk != thr_key) {
         const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
@@ -242,32 +341,98 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         thr = t;
         thr_key = sk;
       }
+      // everything the reload needs is computed BEFORE the wait: between "stage free" and "copy
+      // issued" only three shared-memory stores, the expect_tx and the bulk copy remain
+#if LM_PRUNE_EXP == 2  // experiment: no DRAM traffic (the tiles cycle through an L2-resident 32 MB window)
+      const uint64_t r0 = a.row_first + (tile & 1023) * PTILE_ROWS;
+#else
+      const uint64_t r0 = a.row_first + tile * PTILE_ROWS;
+#endif
+      const uint64_t avail = a.avail_rows > r0 ? a.avail_rows - r0 : 0;
+      const uint32_t nbytes = (avail < tt ? (uint32_t)avail : tt) * 32;
+      const uint8_t* src = a.seq + r0 * 32;
+      uint8_t* dst = raw + (size_t)s * S.raw_bytes;
+      const uint64_t left = a.row_end > r0 ? a.row_end - r0 : 0;
+      const uint32_t valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
+#if LM_PRUNE_PROF
+      const long long p0 = clock64();
+      p_claim += p0 - p00;
+#endif
+      if (it >= NSTAGE) {
+        ring_wait(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
+#if LM_PRUNE_PROF
+        p_wait += clock64() - p0;
+        const long long d0 = clock64();
+#endif
+#if LM_PRUNE_PRODRECHECK
+        drain(s);
+#endif
+#if LM_PRUNE_PROF
+        p_drain += clock64() - d0;
+#endif
+      }
+#if LM_PRUNE_PROF
+      const long long p1 = clock64();
+#endif
       if (lane == 0) {
         ctl->desc[s].tile = tile;
         ctl->desc[s].bias4 = bias4;
         ctl->desc[s].thr = thr;
+        ctl->desc[s].avail = nbytes / 32;
+        ctl->desc[s].valid = valid;
         if (tile < num_tiles) {
-#if LM_PRUNE_EXP == 2  // experiment: no DRAM traffic (every tile re-reads the first few tiles from L2)
-          uint64_t r0 = a.row_first + (tile & 3) * PTILE_ROWS;
-#else
-          uint64_t r0 = a.row_first + tile * PTILE_ROWS;
+          // (generic-proxy writes into the stage -- the consumers' padding of rows past the end of the
+          // sequence -- are fenced by the writers before they release the stage)
+          mbar_expect_tx(&ctl->full[s], nbytes);
+          if (nbytes) tma_load_1d(dst, src, nbytes, &ctl->full[s]);
+#if LM_PRUNE_PROF
+          ctl->t_issue[s] = clock64();
 #endif
-          uint64_t avail = a.avail_rows > r0 ? a.avail_rows - r0 : 0;
-          uint32_t nrows = avail < tt ? (uint32_t)avail : tt;
-          fence_proxy_async();
-          mbar_expect_tx(&ctl->full[s], nrows * 32);
-          if (nrows) tma_load_1d(raw + (size_t)s * S.raw_bytes, a.seq + r0 * 32, nrows * 32, &ctl->full[s]);
         } else {
           mbar_arrive(&ctl->full[s]);  // end marker: consumers read desc.tile >= num_tiles and leave
         }
       }
+      __syncwarp();
+#if LM_PRUNE_PROF
+      p_issue += clock64() - p1;
+#endif
       if (tile >= num_tiles) break;
     }
+#if LM_PRUNE_PROF
+    if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0)
+      printf("cta %d producer: tiles %u  claim+wait+drain %lld (wait_empty %lld drain %lld)  empty->issued %lld cyc/tile %lld\n",
+             blockIdx.x, it, p_claim, p_wait, p_drain, p_issue, it ? p_issue / it : 0);
+#endif
+    // the tiles still in the other stages: wait for their consumers, recheck their candidates
+    for (uint32_t j = 1; j < NSTAGE; ++j) {
+      const uint32_t it2 = it + j;
+      if (it2 < NSTAGE) continue;
+      const int s2 = it2 % NSTAGE;
+      ring_wait(&ctl->empty[s2], ((it2 / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
+#if LM_PRUNE_PRODRECHECK
+      drain(s2);
+#endif
+    }
+    if (lane == 0 && a.stats && n_cand) atomicAdd(&a.stats[0], n_cand);
     if (blockIdx.x == 0 && lane == 0 && a.stats) {
       unsigned long long ns1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
       a.stats[3] = (unsigned long long)(clock64() - clk0);
       a.stats[4] = ns1 - ns0;
+    }
+    if (a.link.world > 1) {
+      // row-sharded scan: the LAST producer warp of the grid to finish (every CTA's winners, hits and
+      // statistics are final by then) hands this GPU's result block to every GPU and raises the flags
+      unsigned long long done = 0;
+      if (lane == 0) {
+        __threadfence();
+        done = atomicAdd(&a.stats[5], 1ull);
+      }
+      done = __shfl_sync(0xffffffffu, done, 0);
+      if (done == (unsigned long long)gridDim.x - 1) {
+        __threadfence();
+        peer_publish(a.link, THR ? a.count - 33 : a.colkeys, lane);
+      }
     }
     return;
   }
@@ -275,7 +440,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   // ===================== consumer warps: warp w filters rows [w * WARP_ROWS, (w + 1) * WARP_ROWS) of
   // every tile and rechecks its own candidates
   const int q = lane & 7, g = lane >> 3;
-  uint32_t* queue = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;
+  uint32_t* const queue0 = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;  // stage 0's queue
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
   // filter tables in per-thread registers.  They are bounced through shared
@@ -284,43 +449,55 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   // values in URs and re-materialise them with a UR->R move before every look-up.
   uint32_t tlo[R], thi[R];
   {
-    if (lane < R) { queue[lane] = a.plan.tab_lo[lane]; queue[16 + lane] = a.plan.tab_hi[lane]; }
+    if (lane < R) { queue0[lane] = a.plan.tab_lo[lane]; queue0[16 + lane] = a.plan.tab_hi[lane]; }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&queue[k]);
-      thi[k] = *reinterpret_cast<volatile uint32_t*>(&queue[16 + k]);
+      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&queue0[k]);
+      thi[k] = *reinterpret_cast<volatile uint32_t*>(&queue0[16 + k]);
     }
     __syncwarp();
   }
   const uint32_t one = a.one;
-  unsigned long long n_cand = 0, n_over = 0;
+  unsigned long long n_over = 0, n_cand = 0;
+#if LM_PRUNE_PROF
+  long long c_wait = 0, c_busy = 0, c_lat = 0, c_nlat = 0, c_t0 = clock64();
+#endif
 
   for (uint32_t it = 0;; ++it) {
     const int s = it % NSTAGE;
-    mbar_wait_backoff(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
+    uint32_t* const queue = queue0 + (uint32_t)s * PW * QCAP;  // this warp's queue for the tile in stage s
+#if LM_PRUNE_PROF
+    const long long w0 = clock64();
+#endif
+    ring_wait(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
+#if LM_PRUNE_PROF
+    const long long w1 = clock64();
+    c_wait += w1 - w0;
+    if (w1 - w0 > 300) { c_lat += w1 - ctl->t_issue[s]; c_nlat += 1; }
+#endif
     const uint64_t tile = ctl->desc[s].tile;
     if (tile >= num_tiles) break;
     const uint32_t bias4 = ctl->desc[s].bias4;
     const float thr = ctl->desc[s].thr;
     const uint32_t wrow0 = warp * WARP_ROWS;                       // this warp's first row in the tile
-    const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;
     uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
     {
       // rows past the readable extent (end of the sequence only): default symbol.  Every warp fills
       // the rows IT reads; overlapping halo rows get the same value from both neighbours.
-      uint64_t avail = a.avail_rows > tile_row0 ? a.avail_rows - tile_row0 : 0;
+      const uint32_t avail = ctl->desc[s].avail;
       const uint32_t wend = wrow0 + WARP_ROWS + ((m + 3) & ~3);
       if (avail < wend) {
-        uint32_t w0 = (avail > wrow0 ? (uint32_t)avail : wrow0) * 8, w1 = wend * 8;
+        uint32_t w0 = (avail > wrow0 ? avail : wrow0) * 8, w1 = wend * 8;
         uint32_t fill = a.pad_fill * 0x01010101u;
         for (uint32_t w = w0 + lane; w < w1; w += 32) reinterpret_cast<uint32_t*>(rawb)[w] = fill;
+        fence_proxy_async();  // these generic-proxy writes precede the next bulk copy into this stage
         __syncwarp();
       }
     }
-    const uint64_t left = a.row_end - tile_row0;  // > 0 for every claimed tile
-    const uint32_t tile_valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
+    const uint32_t tile_valid = ctl->desc[s].valid;  // > 0 for every claimed tile
     const uint32_t rows_valid = tile_valid > wrow0 ? min(tile_valid - wrow0, (uint32_t)WARP_ROWS) : 0;
+    uint32_t nq_pub = 0;  // candidates handed to the producer warp
 
 #if LM_PRUNE_EXP == 1  // experiment: stream the tiles, no filtering
     if (rows_valid && bias4 == 0x12345678u) {
@@ -410,51 +587,82 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
             }
           }
         }
-        uint32_t any = 0;
+        // one test for the whole block; the rare hit narrows it down through 4 sub-blocks of 8 rows
+        // (their ORs are by-products of the reduction) before it looks at row pairs
+        constexpr int NSUB = (G + 7) / 8;
+        uint32_t sub[NSUB];
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u) sub[u] = 0;
 #pragma unroll
         for (int ii = 0; ii < G; ++ii)
-          if (ii < g) any |= acc[ii];
+          if (ii < g) sub[ii >> 3] |= acc[ii];
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u) any |= sub[u];
         if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0)) {
 #pragma unroll
-          for (int ii = 0; ii < G; ii += 2) {
-            if (ii + 1 < g) push2(acc[ii], acc[ii + 1], i0 + ii);
-            else if (ii < g) push2(acc[ii], 0u, i0 + ii);
+          for (int u = 0; u < NSUB; ++u) {
+            if (!__any_sync(0xffffffffu, (sub[u] & 0x80808080u) != 0)) continue;
+#pragma unroll
+            for (int ii = 8 * u; ii < 8 * u + 8 && ii < G; ii += 2) {
+              if (ii + 1 < g) push2(acc[ii], acc[ii + 1], i0 + ii);
+              else if (ii < g) push2(acc[ii], 0u, i0 + ii);
+            }
           }
         }
       }
       __syncwarp();  // queue complete
 
-      // ---- exact recheck of the candidates (or of the warp's whole slice on overflow)
-      if (nq) {
-        if (nq <= QCAP) {
-          for (uint32_t k = lane; k < nq * 8; k += 32) {
-            const uint32_t code = queue[k >> 3], b = k & 7;
-            if (!((code >> b) & 1u)) continue;
-            const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
-            if (row >= tile_valid) continue;
-            float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
-                                   : exact_score(rawb, tab, m_pad, row, col);
-            if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
-          }
-          n_cand += nq;
-        } else {
-          for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
-            uint32_t row = wrow0 + (p >> 5), col = p & 31;
-            float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
-                                   : exact_score(rawb, tab, m_pad, row, col);
-            if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
-          }
-          n_over += 1;
+      const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;  // (only the rare paths below use it)
+#if !LM_PRUNE_PRODRECHECK
+      // ---- exact recheck of the candidates
+      if (nq && nq <= QCAP) {
+        for (uint32_t k = lane; k < nq * 8; k += 32) {
+          const uint32_t code = queue[k >> 3], b = k & 7;
+          if (!((code >> b) & 1u)) continue;
+          const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
+          if (row >= tile_valid) continue;
+          float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
+                                 : exact_score(rawb, tab, m_pad, row, col);
+          if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
         }
+        n_cand += nq;
+        nq = 0;
       }
+#endif
+      // ---- (producer-recheck builds: the candidates stay in the queue for the producer warp, which
+      // rechecks them before it reloads the stage.)  A queue overflow (low-complexity sequence, very
+      // low threshold) makes this warp rescan its whole slice exactly, itself
+      if (nq > QCAP) {
+        for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
+          uint32_t row = wrow0 + (p >> 5), col = p & 31;
+          float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
+                                 : exact_score(rawb, tab, m_pad, row, col);
+          if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
+        }
+        n_over += 1;
+        nq = 0;
+      }
+      nq_pub = nq;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ctl->empty[s]);  // this warp is done with the stage
+#if LM_PRUNE_PROF
+    c_busy += clock64() - w1;
+#endif
+    if (lane == 0) {
+      ctl->nq[s][warp] = nq_pub;
+      mbar_arrive(&ctl->empty[s]);  // this warp is done with the stage (release: queue + count are visible)
+    }
   }
   if (lane == 0 && a.stats) {
-    if (n_cand) atomicAdd(&a.stats[0], n_cand);
     if (n_over) atomicAdd(&a.stats[1], n_over);
+    if (n_cand) atomicAdd(&a.stats[0], n_cand);
   }
+#if LM_PRUNE_PROF
+  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (warp == 0 || warp == 5))
+    printf("cta %d warp %d: total %lld wait_full %lld busy %lld  waits>300cyc %lld mean issue->wake %lld cyc\n", blockIdx.x,
+           warp, clock64() - c_t0, c_wait, c_busy, c_nlat, c_nlat ? c_lat / c_nlat : 0);
+#endif
 }
 
 template <bool THR>

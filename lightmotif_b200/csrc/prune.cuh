@@ -82,8 +82,14 @@ struct PruneArgs {
   unsigned long long cap = 0;
   unsigned long long* count = nullptr;
   // statistics: [0] candidates rechecked, [1] tiles that overflowed to the exact fallback;
-  // [2] is the dynamic tile counter (zero-initialised)
+  // [2] is the dynamic tile counter (zero-initialised), [3] / [4] SM cycles / ns of CTA 0,
+  // [5] counter of finished consumer warps (zero-initialised; the last one publishes to the peers)
   unsigned long long* stats = nullptr;
+  // hit coordinates (threshold mode): row = row relative to row_begin + row_add,
+  // position = col * pos_rows + row  (pos_rows == 0: row_end - row_begin)
+  uint64_t row_add = 0, pos_rows = 0;
+  // row-sharded scans (link.world > 1): shared running maximum + publication of the result block
+  PeerLink link;
 };
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream);

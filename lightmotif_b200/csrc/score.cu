@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
               unsigned long long slot = base + __popc(mask & ((1u << lane) - 1));
               if (slot < a.cap) {
                 lm_hit h;
-                h.row = row - a.row_begin;
+                h.row = row - a.row_begin + a.row_add;
                 h.col = lane;
-                h.position = (uint64_t)lane * n_score_rows + h.row;
+                h.position = (uint64_t)lane * (a.pos_rows ? a.pos_rows : n_score_rows) + h.row;
                 h.score = sc;
                 a.hits[slot] = h;
               }

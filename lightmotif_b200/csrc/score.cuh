@@ -43,6 +43,9 @@ struct ScoreArgs {
   lm_hit* hits = nullptr;
   unsigned long long cap = 0;
   unsigned long long* count = nullptr;
+  // hit coordinates: row = row relative to row_begin + row_add, position = col * pos_rows + row
+  // (pos_rows == 0: row_end - row_begin)
+  uint64_t row_add = 0, pos_rows = 0;
 };
 
 // Enqueue the scoring kernel on `stream`.  is_u8 selects the saturating u8

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.lm_abi_version() == 1
+    assert lib.lm_abi_version() == 2
     assert lib.lm_strerror(-3) == b"not enough wrapping rows for motif"
 
 
