@@ -658,10 +658,13 @@ def run_ours(args):
         comm.close()
         dist.destroy_process_group()
         if rank == 0:
-            time.sleep(0.5)  # let the other ranks' NCCL log lines drain before the JSON line
+            time.sleep(1.5)  # let the other ranks exit (NCCL logs a few lines at unload) before the JSON line
     if line is not None:
         sys.stdout.write("\n" + json.dumps(line) + "\n")
         sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(0)  # the JSON line stays the LAST line of stdout: skip library unload messages of this rank
 
 
 def main():

@@ -332,7 +332,7 @@ int lm_seq_score_threshold_f32_batch(lm_ctx *ctx, const lm_seq *seq,
  *                            (entries 0..3 = tab_lo bytes, 4..7 = tab_hi bytes);
  * and guarantees  c0 + delta * sum_q(p) >= score(p)  in real arithmetic, with
  * |f32 sequential score - real score| <= eps.  A position is rechecked exactly
- * iff sum_q(p) >= ceil((T - eps - c0) / delta) - 1 for the current threshold T.
+ * iff sum_q(p) >= ceil((T - eps - c0) / delta - 1e-6) for the current threshold T.
  * `threshold` is the planning threshold (is_argmax != 0: ignored, the expected
  * maximum over n_positions uniform-random positions is used). */
 typedef struct lm_filter_plan {

@@ -30,7 +30,7 @@
 //
 // The bound:  UB(p) = c0 + delta * sum_q(p) >= real-valued score(p), and the
 // fp32 sequential sum differs from the real sum by at most eps, so
-//   fp32score(p) >= T  ==>  sum_q(p) >= ceil((T - eps - c0) / delta)  (- 1 safety)
+//   fp32score(p) >= T  ==>  sum_q(p) >= ceil((T - eps - c0) / delta - 1e-6)   (1e-6: rounding of the division)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -63,18 +63,18 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #ifndef LM_PRUNE_L2PF
 #define LM_PRUNE_L2PF 0      // L2 prefetch distance in grid rounds (0 = off): tile t + L2PF * gridDim.x
 #endif
-#ifndef LM_PRUNE_PRODRECHECK
-#define LM_PRUNE_PRODRECHECK 0  // 1: the producer warp rechecks the queued candidates (before it reloads the stage)
-#endif
 #ifndef LM_PRUNE_PROF
 #define LM_PRUNE_PROF 0      // 1: CTAs 0 and 77 print a cycle breakdown of their pipeline (diagnostic builds only)
 #endif
 #ifndef LM_PRUNE_WAIT
 #define LM_PRUNE_WAIT 0      // 0: try_wait + nanosleep back-off, 1: plain try_wait loop, 2: try_wait with suspend hint
 #endif
-#ifndef LM_PRUNE_NSTAGE
-#define LM_PRUNE_NSTAGE 2
+#ifndef LM_PRUNE_SPT
+#define LM_PRUNE_SPT 8       // slices (one warp's worth of rows) per staged tile
 #endif
+#ifndef LM_PRUNE_NSTAGE
+#define LM_PRUNE_NSTAGE (16 / LM_PRUNE_SPT)   // 2 x 32 KB per CTA (4 x 16 KB and 8 x 8 KB measured: no faster,
+#endif                                        // the kernel is bound by its integer pipes, not by the ring)
 constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 #ifndef LM_PRUNE_PL
 #define LM_PRUNE_PL 31
@@ -84,7 +84,10 @@ constexpr int NSTAGE = LM_PRUNE_NSTAGE; // tile buffers in flight per CTA
 #endif
 constexpr int PL = LM_PRUNE_PL;        // rows per thread per tile (odd => conflict-free LDS)
 constexpr int WARP_ROWS = 4 * PL;
-constexpr int PTILE_ROWS = PW * WARP_ROWS;
+constexpr int SPT = LM_PRUNE_SPT;          // slices per staged tile
+constexpr int PTILE_ROWS = SPT * WARP_ROWS;
+constexpr int CLAIM = PW / SPT > 0 ? PW / SPT : 1;  // consecutive tiles a producer claims per trip to the global counter
+static_assert(NSTAGE * SPT > PW + SPT - 1 || NSTAGE * SPT >= 2 * PW, "ring too shallow for the slices in flight");
 constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
 
 __device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
@@ -107,7 +110,7 @@ struct PSmem {
 struct Ctl {
   uint64_t full[NSTAGE], empty[NSTAGE];
   struct { unsigned long long tile; uint32_t bias4; float thr; uint32_t avail, valid; } desc[NSTAGE];  // avail: rows the copy delivers; valid: rows of the tile inside the scored range
-  uint32_t nq[NSTAGE][PW];  // candidate-queue lengths of the tile in each stage, per consumer warp
+  uint32_t next_slice;      // slices (WARP_ROWS rows of a tile) handed out to the consumer warps so far
   long long t_issue[NSTAGE];  // LM_PRUNE_PROF: SM clock when the stage's TMA copy was issued
 };
 __host__ __device__ inline PSmem psmem(int m, int tab_stride) {
@@ -116,7 +119,7 @@ __host__ __device__ inline PSmem psmem(int m, int tab_stride) {
   s.table_off = 0;
   s.ctl_off = ((uint32_t)((m + 3) & ~3) * tab_stride * 4 + 127) & ~127u;
   s.queue_off = (s.ctl_off + (uint32_t)sizeof(Ctl) + 127) & ~127u;
-  s.raw_off = s.queue_off + NSTAGE * PW * QCAP * 4;
+  s.raw_off = s.queue_off + PW * QCAP * 4;
   s.raw_bytes = (tt * 32 + 127) & ~127u;
   s.total = s.raw_off + NSTAGE * s.raw_bytes;
   return s;
@@ -177,17 +180,31 @@ __device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel
 // to a multiple of 4 rows with +0.0 (x + 0.0 == x: the chain starts at +0.0 and never yields -0.0).
 __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* tab, int m_pad,
                                              uint32_t row_in_tile, uint32_t col) {
+  // The candidate's warp waits for this chain, and the other warps of the CTA end up waiting for that
+  // warp: keep its latency short.  All symbol loads of a block of 8 motif rows are issued before
+  // the first look-up, all look-ups before the first add; only the adds are sequential (they must be).
   float s = 0.0f;
   const uint8_t* p = rawb + row_in_tile * 32 + col;
-  for (int j = 0; j < m_pad; j += 4) {
+  int j = 0;
+  for (; j + 8 <= m_pad; j += 8) {
+    uint32_t sy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sy[k] = p[32 * k];
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = tab[8 * k + sy[k]];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, w[k]);
+    p += 256;
+    tab += 64;
+  }
+  if (j < m_pad) {  // m_pad is a multiple of 4
     const uint32_t s0 = p[0], s1 = p[32], s2 = p[64], s3 = p[96];
     const float w0 = tab[s0], w1 = tab[8 + s1], w2 = tab[16 + s2], w3 = tab[24 + s3];
     s = __fadd_rn(s, w0);
     s = __fadd_rn(s, w1);
     s = __fadd_rn(s, w2);
     s = __fadd_rn(s, w3);
-    p += 128;
-    tab += 32;
   }
   return s;
 }
@@ -218,8 +235,9 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&ctl->full[s], 1);
-      mbar_init(&ctl->empty[s], PW);
+      mbar_init(&ctl->empty[s], SPT);
     }
+    ctl->next_slice = 0;
     mbar_fence_init();
   }
   const int m_pad = (m + 3) & ~3;
@@ -239,68 +257,30 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       clk0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
     }
-    // Exact recheck of the candidates the consumer warps queued for the tile in stage s (sequential
-    // f32 sum in the reference's order, from the tile still in shared memory).  It runs HERE, on the
-    // otherwise idle producer warp, between "all consumers are done with the stage" and its reload:
-    // the filter warps never leave their uniform fast path for it, so they stay in step with each
-    // other and the 2-deep tile ring does not stall on the one warp that found a candidate.
-    unsigned long long n_cand = 0;
-    uint32_t* const queues = reinterpret_cast<uint32_t*>(smem + S.queue_off);
-    auto drain = [&](int s) {
-      uint32_t cnt = lane < PW ? ctl->nq[s][lane] : 0u;
-      uint32_t incl = cnt;
-#pragma unroll
-      for (int o = 1; o < PW; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      uint32_t ends[PW];
-#pragma unroll
-      for (int j = 0; j < PW; ++j) ends[j] = __shfl_sync(0xffffffffu, incl, j);
-      const uint32_t total = ends[PW - 1];
-      if (total == 0) return;
-      n_cand += total;
-      const uint64_t tile = ctl->desc[s].tile;
-      const float dthr = ctl->desc[s].thr;
-      const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;
-      const uint64_t left = a.row_end - tile_row0;
-      const uint32_t tile_valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
-      const uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
-      for (uint32_t g = lane; g < total * 8; g += 32) {
-        const uint32_t e = g >> 3, b = g & 7;
-        uint32_t w = 0, first = 0;  // queue (= consumer warp) holding entry e, and its first entry
-#pragma unroll
-        for (int j = 0; j < PW - 1; ++j)
-          if (e >= ends[j]) { w = j + 1; first = ends[j]; }
-        const uint32_t code = queues[((uint32_t)s * PW + w) * QCAP + (e - first)];
-        if (!((code >> b) & 1u)) continue;
-        const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
-        if (row >= tile_valid) continue;
-        const float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
-                                     : exact_score(rawb, tab, m_pad, row, col);
-        if (sc >= dthr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
-      }
-      __syncwarp();
-    };
 #if LM_PRUNE_PROF
     long long p_wait = 0, p_drain = 0, p_issue = 0, p_claim = 0;
 #endif
-    uint32_t it = 0;
+    uint32_t it = 0, sk_last = 0, n_end = 0, first_end = 0;
+    unsigned long long claim_base = 0;
     for (;; ++it) {
       const int s = it % NSTAGE;
 #if LM_PRUNE_PROF
       const long long p00 = clock64();
 #endif
       // claim the tile and fetch the running maximum first: both round trips overlap the wait
-      unsigned long long tile = 0;
-      if (lane == 0) tile = atomicAdd(&a.stats[2], 1ull);
-      uint32_t sk = 0;
-      if (!THR) {
-        sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
-        // row-sharded scan: the maximum the OTHER GPUs have found so far (pushed over NVLink)
-        if (a.link.world > 1 && lane == 0) sk = max(sk, peer_floor_key(a.link));
+      // (CLAIM consecutive tiles per trip: the tiles are small, the L2 round trip is not)
+      unsigned long long tile = claim_base + it % CLAIM;
+      uint32_t sk = sk_last;
+      if (it % CLAIM == 0) {
+        if (lane == 0) tile = atomicAdd(&a.stats[2], (unsigned long long)CLAIM);
+        if (!THR) {
+          sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
+          // row-sharded scan: the maximum the OTHER GPUs have found so far (pushed over NVLink)
+          if (a.link.world > 1 && lane == 0) sk = max(sk, peer_floor_key(a.link));
+        }
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        claim_base = tile;
       }
-      tile = __shfl_sync(0xffffffffu, tile, 0);
 #if LM_PRUNE_L2PF > 0
       // the tile some CTA will claim L2PF grid rounds from now: start its trip from HBM to L2 already
       if (lane == 0) {
@@ -311,7 +291,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         }
       }
 #endif
-      if (!THR) {
+      if (!THR && it % CLAIM == 0) {
         uint32_t own = lane == 0 && a.link.world > 1 ? (uint32_t)(__ldcg(&a.colkeys[0]) >> 32) : sk;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -323,17 +303,18 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           if (own > peer_floor_key(a.link) || pushed_key == 0) peer_push_floor(a.link, own, lane);
           pushed_key = own;
         }
+        sk_last = sk;
       }
       // ---- current threshold -> byte bias (recomputed only when the threshold moved)
       if (THR ? it == 0 : sk != thr_key) {
         const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
-        // sum_q >= qthr is implied by fp32score >= t (see header); -1 guards the division
+        // sum_q >= qthr is implied by fp32score >= t (see header); 1e-6 guards the division
         double need = ((double)t - a.plan.eps - a.plan.c0) / a.plan.delta;
         int bias;
         if (!(need > 1.0)) bias = 128;                               // everything passes
         else if (need > (double)a.plan.smax + 2.0) bias = 0;         // nothing can pass
         else {
-          int qthr = (int)ceil(need) - 1;
+          int qthr = (int)ceil(need - 1e-6);
           qthr = qthr < 1 ? 1 : (qthr > 128 ? 128 : qthr);
           bias = 128 - qthr;
         }
@@ -364,9 +345,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         p_wait += clock64() - p0;
         const long long d0 = clock64();
 #endif
-#if LM_PRUNE_PRODRECHECK
-        drain(s);
-#endif
 #if LM_PRUNE_PROF
         p_drain += clock64() - d0;
 #endif
@@ -396,24 +374,25 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
 #if LM_PRUNE_PROF
       p_issue += clock64() - p1;
 #endif
-      if (tile >= num_tiles) break;
+      // past the end: keep handing out end markers until every consumer warp has met one (the slices
+      // of a tile go to whichever warps are free, so up to PW further slices may have been taken)
+      if (tile >= num_tiles) {
+        if (n_end == 0) first_end = it;
+        if (++n_end > (uint32_t)((PW + SPT - 1) / SPT)) break;
+      }
     }
 #if LM_PRUNE_PROF
-    if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0)
+    if (blockIdx.x == 0 && lane == 0)
       printf("cta %d producer: tiles %u  claim+wait+drain %lld (wait_empty %lld drain %lld)  empty->issued %lld cyc/tile %lld\n",
              blockIdx.x, it, p_claim, p_wait, p_drain, p_issue, it ? p_issue / it : 0);
 #endif
-    // the tiles still in the other stages: wait for their consumers, recheck their candidates
-    for (uint32_t j = 1; j < NSTAGE; ++j) {
-      const uint32_t it2 = it + j;
+    // wait until the consumers are done with the tiles still in the other stages: after that this
+    // CTA's winners, hits and statistics are final
+    for (uint32_t it2 = it + 1; it2 < first_end + NSTAGE; ++it2) {
       if (it2 < NSTAGE) continue;
       const int s2 = it2 % NSTAGE;
       ring_wait(&ctl->empty[s2], ((it2 / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
-#if LM_PRUNE_PRODRECHECK
-      drain(s2);
-#endif
     }
-    if (lane == 0 && a.stats && n_cand) atomicAdd(&a.stats[0], n_cand);
     if (blockIdx.x == 0 && lane == 0 && a.stats) {
       unsigned long long ns1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
@@ -440,7 +419,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   // ===================== consumer warps: warp w filters rows [w * WARP_ROWS, (w + 1) * WARP_ROWS) of
   // every tile and rechecks its own candidates
   const int q = lane & 7, g = lane >> 3;
-  uint32_t* const queue0 = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;  // stage 0's queue
+  uint32_t* const queue = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
   // filter tables in per-thread registers.  They are bounced through shared
@@ -449,12 +428,12 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   // values in URs and re-materialise them with a UR->R move before every look-up.
   uint32_t tlo[R], thi[R];
   {
-    if (lane < R) { queue0[lane] = a.plan.tab_lo[lane]; queue0[16 + lane] = a.plan.tab_hi[lane]; }
+    if (lane < R) { queue[lane] = a.plan.tab_lo[lane]; queue[16 + lane] = a.plan.tab_hi[lane]; }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&queue0[k]);
-      thi[k] = *reinterpret_cast<volatile uint32_t*>(&queue0[16 + k]);
+      tlo[k] = *reinterpret_cast<volatile uint32_t*>(&queue[k]);
+      thi[k] = *reinterpret_cast<volatile uint32_t*>(&queue[16 + k]);
     }
     __syncwarp();
   }
@@ -462,11 +441,19 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   unsigned long long n_over = 0, n_cand = 0;
 #if LM_PRUNE_PROF
   long long c_wait = 0, c_busy = 0, c_lat = 0, c_nlat = 0, c_t0 = clock64();
+  int hist[6] = {0, 0, 0, 0, 0, 0};
 #endif
 
-  for (uint32_t it = 0;; ++it) {
+  for (;;) {
+    // The SPT slices of a tile (WARP_ROWS rows each) are not tied to warps: a free consumer warp takes
+    // the next slice of the CTA's tile sequence.  A warp that had candidates to recheck simply takes
+    // its next slice a little later while the others carry on.  At most PW slices are in flight,
+    // spanning fewer than NSTAGE consecutive tiles, so the parity waits below cannot alias.
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(&ctl->next_slice, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    const uint32_t it = idx / SPT;
     const int s = it % NSTAGE;
-    uint32_t* const queue = queue0 + (uint32_t)s * PW * QCAP;  // this warp's queue for the tile in stage s
 #if LM_PRUNE_PROF
     const long long w0 = clock64();
 #endif
@@ -475,12 +462,16 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     const long long w1 = clock64();
     c_wait += w1 - w0;
     if (w1 - w0 > 300) { c_lat += w1 - ctl->t_issue[s]; c_nlat += 1; }
+    {
+      const long long dw = w1 - w0;
+      hist[dw < 100 ? 0 : dw < 300 ? 1 : dw < 1000 ? 2 : dw < 2000 ? 3 : dw < 4000 ? 4 : 5] += 1;
+    }
 #endif
     const uint64_t tile = ctl->desc[s].tile;
     if (tile >= num_tiles) break;
     const uint32_t bias4 = ctl->desc[s].bias4;
     const float thr = ctl->desc[s].thr;
-    const uint32_t wrow0 = warp * WARP_ROWS;                       // this warp's first row in the tile
+    const uint32_t wrow0 = (idx % SPT) * WARP_ROWS;                  // first row of the slice in the tile
     uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
     {
       // rows past the readable extent (end of the sequence only): default symbol.  Every warp fills
@@ -497,7 +488,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     }
     const uint32_t tile_valid = ctl->desc[s].valid;  // > 0 for every claimed tile
     const uint32_t rows_valid = tile_valid > wrow0 ? min(tile_valid - wrow0, (uint32_t)WARP_ROWS) : 0;
-    uint32_t nq_pub = 0;  // candidates handed to the producer warp
 
 #if LM_PRUNE_EXP == 1  // experiment: stream the tiles, no filtering
     if (rows_valid && bias4 == 0x12345678u) {
@@ -599,7 +589,11 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         uint32_t any = 0;
 #pragma unroll
         for (int u = 0; u < NSUB; ++u) any |= sub[u];
+#if LM_PRUNE_EXP == 4  // experiment: never leave the fast path (wrong results; shows what the candidates cost)
+        if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0) && bias4 == 0x12345678u) {
+#else
         if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0)) {
+#endif
 #pragma unroll
           for (int u = 0; u < NSUB; ++u) {
             if (!__any_sync(0xffffffffu, (sub[u] & 0x80808080u) != 0)) continue;
@@ -614,8 +608,8 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       __syncwarp();  // queue complete
 
       const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;  // (only the rare paths below use it)
-#if !LM_PRUNE_PRODRECHECK
-      // ---- exact recheck of the candidates
+      // ---- exact recheck of the candidates (sequential f32 sum in the reference's order, from the
+      // tile still in shared memory)
       if (nq && nq <= QCAP) {
         for (uint32_t k = lane; k < nq * 8; k += 32) {
           const uint32_t code = queue[k >> 3], b = k & 7;
@@ -627,12 +621,9 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
         }
         n_cand += nq;
-        nq = 0;
       }
-#endif
-      // ---- (producer-recheck builds: the candidates stay in the queue for the producer warp, which
-      // rechecks them before it reloads the stage.)  A queue overflow (low-complexity sequence, very
-      // low threshold) makes this warp rescan its whole slice exactly, itself
+      // ---- a queue overflow (low-complexity sequence, very low threshold) makes the warp rescan the
+      // whole slice exactly
       if (nq > QCAP) {
         for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
           uint32_t row = wrow0 + (p >> 5), col = p & 31;
@@ -641,27 +632,24 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
         }
         n_over += 1;
-        nq = 0;
       }
-      nq_pub = nq;
     }
     __syncwarp();
 #if LM_PRUNE_PROF
     c_busy += clock64() - w1;
 #endif
-    if (lane == 0) {
-      ctl->nq[s][warp] = nq_pub;
-      mbar_arrive(&ctl->empty[s]);  // this warp is done with the stage (release: queue + count are visible)
-    }
+    if (lane == 0) mbar_arrive(&ctl->empty[s]);  // one more slice of the stage is done
   }
   if (lane == 0 && a.stats) {
     if (n_over) atomicAdd(&a.stats[1], n_over);
     if (n_cand) atomicAdd(&a.stats[0], n_cand);
   }
 #if LM_PRUNE_PROF
-  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (warp == 0 || warp == 5))
-    printf("cta %d warp %d: total %lld wait_full %lld busy %lld  waits>300cyc %lld mean issue->wake %lld cyc\n", blockIdx.x,
-           warp, clock64() - c_t0, c_wait, c_busy, c_nlat, c_nlat ? c_lat / c_nlat : 0);
+  if (blockIdx.x == 0 && lane == 0)
+    printf("cta %d warp %d: total %lld wait_full %lld busy %lld  waits>300cyc %lld mean issue->wake %lld cyc  wait histogram "
+           "<100 %d <300 %d <1000 %d <2000 %d <4000 %d >=4000 %d\n", blockIdx.x,
+           warp, clock64() - c_t0, c_wait, c_busy, c_nlat, c_nlat ? c_lat / c_nlat : 0, hist[0], hist[1], hist[2], hist[3],
+           hist[4], hist[5]);
 #endif
 }
 
@@ -849,7 +837,7 @@ bool quantise_units(Unit* u, int R, double clamp, double restmax, double t_plan,
   out.delta = delta;
   out.c0 = base_sum + restmax;
   const double need = (t_plan - eps - out.c0) / delta;
-  const int qthr = need > 1.0 ? (int)std::ceil(need) - 1 : 0;
+  const int qthr = need > 1.0 ? (int)std::ceil(need - 1e-6) : 0;
   if (qthr <= 0) out.pass = 1.0;
   else if (qthr > smax) out.pass = 0.0;
   else {

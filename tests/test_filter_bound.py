@@ -2,7 +2,7 @@
 integer upper bound the kernel computes must dominate the score,
 
     c0 + delta * sum_q(window) >= score(window)                (real arithmetic)
-    sum_q(window) >= ceil((s32 - eps - c0) / delta) - 1         (what the kernel tests, with T = s32)
+    sum_q(window) >= ceil((s32 - eps - c0) / delta - 1e-6)        (what the kernel tests, with T = s32)
 
 where s32 is the reference's sequential f32 sum -- i.e. a position can never be filtered out at a
 threshold its own exact score reaches.  This is what makes the fused results bit-identical to scoring
@@ -94,7 +94,7 @@ def test_bound_dominates_score(m, kind, mode):
             assert np.all(ub >= real - 1e-9), (lookups, thr, float((real - ub).max()))
             finite = np.isfinite(s32)
             assert np.all(np.abs(s32[finite].astype(np.float64) - real[finite]) <= plan["eps"])
-            need = np.ceil((s32[finite].astype(np.float64) - plan["eps"] - plan["c0"]) / plan["delta"]) - 1
+            need = np.ceil((s32[finite].astype(np.float64) - plan["eps"] - plan["c0"]) / plan["delta"] - 1e-6)
             assert np.all(sq[finite] >= need), (lookups, thr)
             checked += 1
     assert checked >= 2 or (mode == 2 and m < 5)  # paired look-ups need at least 5 motif rows
@@ -151,7 +151,7 @@ def test_protein_bound_dominates_score(m, kind):
                 sq += tab[cls[win[:, plan["j0"] + k]]]
             assert np.all(plan["c0"] + plan["delta"] * sq >= real - 1e-9)
             finite = np.isfinite(s32)
-            need = np.ceil((s32[finite].astype(np.float64) - plan["eps"] - plan["c0"]) / plan["delta"]) - 1
+            need = np.ceil((s32[finite].astype(np.float64) - plan["eps"] - plan["c0"]) / plan["delta"] - 1e-6)
             assert np.all(sq[finite] >= need)
             checked += 1
     assert checked >= 2
