@@ -200,7 +200,7 @@ int upload_table(lm_ctx* ctx, int alphabet, const void* pssm, size_t m, size_t s
 int limits_ok(int alphabet, size_t m) {
   // shared-memory budget of score.cu (table + tile buffers <= 200 KB)
   size_t mp = table_mpad(m);
-  size_t total = mp * table_kp(alphabet) * 4 + (128 + mp) * (32 * 3 + 4) + 4096;
+  size_t total = mp * table_kp(alphabet) * 4 + (128 + mp) * (32 * 3 + 4) + 4096 + mp * 128;  // (+ pair table)
   return total <= 200 * 1024 ? LM_OK : LM_ERR_UNSUPPORTED;
 }
 

@@ -30,6 +30,17 @@
 //      The kernel is bound by the shared-memory pipe (1 warp-LDS/clk/SM).
 //   4. epilogue per tile: coalesced 128-B stores and/or running per-column
 //      best (>=, so the last row wins ties) and/or ballot-compacted hits.
+//
+// Paired positions (DNA f32, tiles without the default symbol N).  Step 3 costs one LDS.32 and one
+// FADD per cell update: the LSU delivers 32 look-ups/clk/SM and the issue ports carry 2.3
+// instructions per update, and the kernel sits at ~72 % of the former because of the latter.  Two
+// ADJACENT positions of a thread (rows i, i + 1 of its column) read adjacent symbols for the same
+// motif row, so a second table  T2[j][s + 4 s'] = (w_j[s], w_j[s'])  (16 float2 entries = 128 bytes
+// = one bank pass per motif row, built in shared memory by the kernel itself) delivers both weights
+// with ONE LDS.64, and ONE packed add (add.rn.f32x2: two independent IEEE adds) applies them to the
+// accumulator pair: half the instructions per update, the same sequential order per position --
+// still bit-identical.  The pair codes 8 s + 32 s' come from the pre-multiplied window words with
+// a funnel shift and a multiply-add per 4 symbols.
 #include "score.cuh"
 
 namespace lm {
@@ -47,7 +58,7 @@ constexpr int TILE_ROWS = WARPS * RPT;  // 128
 constexpr int NWIN = (RPT + 3 + 3) / 4; // 5 window words: rows i + jj, i < 16, jj < 4
 
 struct SmemLayout {
-  uint32_t table_bytes, tilet_off, tsw, raw_off, raw_bytes, bar_off, red_off, total;
+  uint32_t table_bytes, tilet_off, tsw, raw_off, raw_bytes, bar_off, red_off, table2_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int kp, int m_pad) {
@@ -62,7 +73,8 @@ __host__ __device__ inline SmemLayout smem_layout(int kp, int m_pad) {
   L.raw_bytes = tt * 32;
   L.bar_off = L.raw_off + 2 * L.raw_bytes;
   L.red_off = L.bar_off + 16;
-  L.total = L.red_off + WARPS * 32 * 8;
+  L.table2_off = (L.red_off + WARPS * 32 * 8 + 511) & ~511u;  // pair table [m_pad][16] float2 (DNA f32 only)
+  L.total = L.table2_off + (kp == 16 ? (uint32_t)m_pad * 128 : 0);
   return L;
 }
 
@@ -96,6 +108,31 @@ __device__ __forceinline__ void row_step(float (&accf)[RPT], uint32_t (&accu)[RP
   }
 }
 
+// ---- paired positions: acc2[k] = (accumulator of position 2k, of position 2k + 1) as f32x2
+template <int IMM>
+__device__ __forceinline__ void pair_lookup_add(unsigned long long& acc, uint32_t pword, uint32_t group_base,
+                                                uint32_t sel) {
+  uint32_t addr;
+  unsigned long long v;
+  asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(addr) : "r"(pword), "r"(group_base), "r"(sel));
+  asm volatile("ld.shared.b64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(IMM));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(v));
+}
+template <int JJ>
+__device__ __forceinline__ void pair_row_step(unsigned long long (&acc2)[RPT / 2], const uint32_t (&P)[NWIN],
+                                              uint32_t gbase2) {
+#pragma unroll
+  for (int i = 0; i < RPT; i += 2) {
+    const int b = i + JJ;  // window byte of (position i, motif row 4*j4 + JJ); its pair code covers bytes b, b + 1
+    pair_lookup_add<JJ * 128>(acc2[i >> 1], P[b >> 2], gbase2, 0x7650u | (b & 3));
+  }
+}
+// pair codes 8 s + 32 s' of 4 window symbols and their successors, from the pre-multiplied words
+// (bytes 4 s): 2 * w + 8 * (w shifted down one byte); no carries between bytes while s, s' <= 3
+__device__ __forceinline__ uint32_t pair_codes(uint32_t w, uint32_t w_next) {
+  return 2u * w + 8u * __funnelshift_r(w, w_next, 8);
+}
+
 template <int KP, int MODE, bool U8>
 __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(const ScoreArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -111,6 +148,8 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
   const int warp = tid >> 5;
   const uint32_t tt_max = TILE_ROWS + a.m_pad;
   const uint64_t n_score_rows = a.row_end - a.row_begin;
+  constexpr bool PAIRS = KP == 16 && !U8;  // the paired-position path exists for DNA f32
+  float2* table2 = reinterpret_cast<float2*>(smem + L.table2_off);
   constexpr uint32_t SYM_MASK = (KP == 16) ? 0x0f0f0f0fu : 0x1f1f1f1fu;
 
   if (tid == 0) {
@@ -158,6 +197,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
       }
     }
     // ---- transpose to column-major, symbols pre-multiplied by 4
+    uint32_t seen = 0;  // OR of the symbols this thread moves (bit 2 of a byte: the default symbol N)
     {
       const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(rawb);
       const uint32_t nblk = (tt_max / 4) * 8;
@@ -171,6 +211,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
         uint32_t x = prmt(w0, w1, 0x7362), y = prmt(w2, w3, 0x7362);
         uint32_t t0 = prmt(u, v, 0x5410), t1 = prmt(u, v, 0x7632);
         uint32_t t2 = prmt(x, y, 0x5410), t3 = prmt(x, y, 0x7632);
+        if (PAIRS) seen |= w0 | w1 | w2 | w3;
         uint32_t* dst = tilet + (4 * cb) * L.tsw + rb;
         dst[0 * L.tsw] = (t0 & SYM_MASK) << 2;
         dst[1 * L.tsw] = (t1 & SYM_MASK) << 2;
@@ -178,7 +219,10 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
         dst[3 * L.tsw] = (t3 & SYM_MASK) << 2;
       }
     }
-    __syncthreads();
+    // tiles holding an N anywhere (sequence ends, assembly gaps) take the one-look-up-per-update path
+    bool use_pairs = false;
+    if (PAIRS) use_pairs = !__syncthreads_or((seen & 0x04040404u) != 0) && a.n_motifs == 1;
+    else __syncthreads();
 
     const uint32_t* colp = tilet + lane * L.tsw + warp * (RPT / 4);
     const uint64_t my_row0 = tile_row0 + (uint64_t)warp * RPT;  // absolute striped row of acc[0]
@@ -191,6 +235,13 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
         if (it == 0 || a.n_motifs > 1) {
           if (a.n_motifs > 1) __syncthreads();  // previous motif's look-ups are done
           for (int w = tid; w < m_pad * KP; w += THREADS) table[w] = src[w];
+          if (PAIRS && a.n_motifs == 1) {
+            const float* tf = reinterpret_cast<const float*>(src);
+            for (int e = tid; e < m_pad * 16; e += THREADS) {
+              const int j = e >> 4, s0 = e & 3, s1 = (e >> 2) & 3;
+              table2[e] = make_float2(tf[j * KP + s0], tf[j * KP + s1]);
+            }
+          }
           __syncthreads();
         }
       }
@@ -201,6 +252,32 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
       uint32_t W[NWIN];
 #pragma unroll
       for (int k = 0; k < NWIN - 1; ++k) W[k] = colp[k];
+      if (PAIRS && use_pairs) {
+        unsigned long long acc2[RPT / 2];
+#pragma unroll
+        for (int k = 0; k < RPT / 2; ++k) acc2[k] = 0ull;  // (+0.0, +0.0)
+        uint32_t P[NWIN];
+#pragma unroll
+        for (int k = 0; k < NWIN - 2; ++k) P[k] = pair_codes(W[k], W[k + 1]);
+        uint32_t gbase2 = smem_u32(table2);
+        for (int j4 = 0; j4 < m_pad / 4; ++j4) {
+          W[NWIN - 1] = colp[j4 + NWIN - 1];
+          P[NWIN - 2] = pair_codes(W[NWIN - 2], W[NWIN - 1]);
+          P[NWIN - 1] = pair_codes(W[NWIN - 1], 0u);  // only its first two codes (bytes 16, 17) are used
+          pair_row_step<0>(acc2, P, gbase2);
+          pair_row_step<1>(acc2, P, gbase2);
+          pair_row_step<2>(acc2, P, gbase2);
+          pair_row_step<3>(acc2, P, gbase2);
+#pragma unroll
+          for (int k = 0; k < NWIN - 1; ++k) { W[k] = W[k + 1]; P[k] = P[k + 1]; }
+          gbase2 += 4 * 128;
+        }
+#pragma unroll
+        for (int k = 0; k < RPT / 2; ++k) {
+          accf[2 * k] = __uint_as_float((uint32_t)acc2[k]);
+          accf[2 * k + 1] = __uint_as_float((uint32_t)(acc2[k] >> 32));
+        }
+      } else {
       uint32_t gbase = smem_u32(table);
       for (int j4 = 0; j4 < m_pad / 4; ++j4) {
         W[NWIN - 1] = colp[j4 + NWIN - 1];
@@ -211,6 +288,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
 #pragma unroll
         for (int k = 0; k < NWIN - 1; ++k) W[k] = W[k + 1];
         gbase += 4 * KP * 4;
+      }
       }
 
       // ---- epilogue

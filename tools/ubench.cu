@@ -378,6 +378,11 @@ int main() {
     run("lds.32 21-row (protein)", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<1><<<g, t, s>>>(it, 21, 132, o, r); });
     run("lds.64 5-row [x2 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<2><<<g, t, s>>>(it, 5, 96, o, r); });
     run("lds.128 5-row [x4 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<4><<<g, t, s>>>(it, 5, 112, o, r); });
+    run("lds.32 16 entries x 4 B", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<1><<<g, t, s>>>(it, 16, 4, o, r); });
+    run("lds.64 16 entries x 8 B [x2 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<2><<<g, t, s>>>(it, 16, 8, o, r); });
+    run("lds.64 25 entries x 8 B [x2 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<2><<<g, t, s>>>(it, 25, 8, o, r); });
+    run("lds.128 8 entries x 16 B [x4 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<4><<<g, t, s>>>(it, 8, 16, o, r); });
+    run("lds.128 16 entries x 16 B [x4 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<4><<<g, t, s>>>(it, 16, 16, o, r); });
     run("lds.128 1-row [x4 values]", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds<4><<<g, t, s>>>(it, 1, 112, o, r); });
     run("lds.32 random 4096", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds_rand<<<g, t, s>>>(it, 4096, o, r); });
     run("lds.32 random 16384", threads, bl, nsm, OPS, IT, SM, [&](int g, int t, size_t s, int it, float* o, Res* r) { k_lds_rand<<<g, t, s>>>(it, 16384, o, r); });
