@@ -309,6 +309,21 @@ int lm_seq_score_argmax_f32_batch(lm_ctx *ctx, const lm_seq *seq,
                                   const float *pssms, const uint32_t *widths,
                                   const uint64_t *offsets, size_t n_motifs,
                                   size_t pssm_stride, int rule, lm_hit *best);
+/* The same with strand selection (DNA; pwm/mod.rs:566-577 ScoringMatrix::reverse_complement: rows
+ * reversed, A<->T, C<->G): LM_STRAND_DIRECT scans the matrices as given, LM_STRAND_REVERSE their
+ * reverse complements, LM_STRAND_BOTH both -- results are then interleaved, best[2i] = direct,
+ * best[2i + 1] = reverse complement of motif i.  status (nullable, same length as best) receives
+ * LM_OK or LM_EMPTY (motif longer than the sequence: the reference's `None`) per entry. */
+#define LM_STRAND_DIRECT 1
+#define LM_STRAND_REVERSE 2
+#define LM_STRAND_BOTH 3
+int lm_seq_score_argmax_f32_batch_rc(lm_ctx *ctx, const lm_seq *seq,
+                                     const float *pssms, const uint32_t *widths,
+                                     const uint64_t *offsets, size_t n_motifs,
+                                     size_t pssm_stride, int strands, int rule,
+                                     lm_hit *best, int *status);
+/* out = reverse complement of a DNA matrix ([m][pssm_stride], columns A,C,T,G,N); host only */
+int lm_pssm_reverse_complement(const float *pssm, size_t m, size_t pssm_stride, float *out);
 /* Same job loop with one threshold per motif (what the CLI computes from a
  * p-value, lightmotif-cli/src/main.rs:468-497): hits of motif i go to
  * hits[i * cap ..] in row-major order, counts[i] = total number of hits of
@@ -320,6 +335,15 @@ int lm_seq_score_threshold_f32_batch(lm_ctx *ctx, const lm_seq *seq,
                                      const uint64_t *offsets, size_t n_motifs,
                                      size_t pssm_stride, const float *thresholds,
                                      lm_hit *hits, size_t cap, size_t *counts);
+
+/* with strand selection: hits / counts of entry e (= motif for one strand, 2 * motif + strand for
+ * LM_STRAND_BOTH) at hits[e * cap ..] / counts[e]; thresholds stay one per motif */
+int lm_seq_score_threshold_f32_batch_rc(lm_ctx *ctx, const lm_seq *seq,
+                                        const float *pssms, const uint32_t *widths,
+                                        const uint64_t *offsets, size_t n_motifs,
+                                        size_t pssm_stride, int strands,
+                                        const float *thresholds, lm_hit *hits,
+                                        size_t cap, size_t *counts);
 
 /* The filter the fused DNA calls would use for `pssm` (host only, no GPU
  * needed): introspection for tests and tuning.  The kernel computes, per

@@ -17,11 +17,12 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .capi import (DNA, PROTEIN, RULE_AVX2, RULE_GENERIC, RULE_SSE2, LANES, ColWin, Hit,
-                   LightmotifError)
+from .capi import (DNA, PROTEIN, RULE_AVX2, RULE_GENERIC, RULE_SSE2, STRAND_DIRECT, STRAND_REVERSE, STRAND_BOTH,
+                   LANES, ColWin, Hit, LightmotifError)
 
 __all__ = ["Pipeline", "DeviceSequence", "Comm", "InvalidSymbol", "UnsupportedBackend", "MatrixCoordinates",
-           "DNA", "PROTEIN", "RULE_GENERIC", "RULE_AVX2", "RULE_SSE2", "LANES", "alphabet_k",
+           "DNA", "PROTEIN", "RULE_GENERIC", "RULE_AVX2", "RULE_SSE2", "STRAND_DIRECT", "STRAND_REVERSE", "STRAND_BOTH",
+           "reverse_complement", "LANES", "alphabet_k",
            "pad_pssm", "aligned_empty", "argmax_merge", "COLWIN_DTYPE", "HIT_DTYPE"]
 
 
@@ -223,39 +224,47 @@ class DeviceSequence:
             at += len(p)
         return flat, widths, offs, stride
 
-    def score_threshold_batch(self, pssms, thresholds, cap=4096, counts_only=False):
-        """Many motifs, one threshold each (lm_seq_score_threshold_f32_batch) -> list of hit lists
-        (or, with counts_only, just the number of hits per motif)."""
+    def score_threshold_batch(self, pssms, thresholds, cap=4096, counts_only=False, strands=capi.STRAND_DIRECT):
+        """Many motifs, one threshold each (lm_seq_score_threshold_f32_batch_rc) -> list of hit lists
+        (or, with counts_only, just the number of hits per entry).  strands = STRAND_BOTH scans every
+        motif and its reverse complement: entries 2i (direct) and 2i + 1 (reverse complement)."""
         flat, widths, offs, stride = self._flatten(pssms)
         thr = np.ascontiguousarray(thresholds, dtype=np.float32)
         assert thr.size == len(pssms)
-        hits = (Hit * (len(pssms) * cap))()
-        counts = (C.c_size_t * len(pssms))()
-        st = capi.lib().lm_seq_score_threshold_f32_batch(self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs),
-                                                         len(pssms), stride, _ptr(thr), hits, cap, counts)
+        n = len(pssms) * (2 if strands == capi.STRAND_BOTH else 1)
+        hits = np.zeros(n * cap, dtype=HIT_DTYPE)
+        counts = (C.c_size_t * n)()
+        st = capi.lib().lm_seq_score_threshold_f32_batch_rc(self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs),
+                                                            len(pssms), stride, strands, _ptr(thr),
+                                                            hits.ctypes.data_as(C.POINTER(Hit)), cap, counts)
         if counts_only and st in (capi.OK, capi.ERR_OVERFLOW):
             return [int(c) for c in counts]
         if st == capi.ERR_OVERFLOW:
-            return self.score_threshold_batch(pssms, thresholds, cap=max(counts))
+            return self.score_threshold_batch(pssms, thresholds, cap=max(counts), strands=strands)
         self._pli._check(st)
-        return [[_hit(hits[q * cap + i]) for i in range(counts[q])] for q in range(len(pssms))]
+        return [[{"row": int(h["row"]), "col": int(h["col"]), "position": int(h["position"]), "score": float(h["score"])}
+                 for h in hits[q * cap:q * cap + counts[q]]] for q in range(n)]
 
-    def score_argmax_batch(self, pssms, rule=RULE_AVX2):
-        """Many motifs over this sequence (the lightmotif-cli job loop)."""
-        k = alphabet_k(self.alphabet)
-        stride = pad_pssm(np.zeros((1, k), np.float32), self.alphabet)[1]
-        widths = np.array([len(p) for p in pssms], dtype=np.uint32)
-        offs = np.zeros(len(pssms), dtype=np.uint64)
-        flat = np.zeros((int(widths.sum()), stride), dtype=np.float32)
-        at = 0
-        for i, p in enumerate(pssms):
-            offs[i] = at * stride
-            flat[at:at + len(p), :k] = np.asarray(p, dtype=np.float32)
-            at += len(p)
-        best = (Hit * len(pssms))()
-        self._pli._check(capi.lib().lm_seq_score_argmax_f32_batch(
-            self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs), len(pssms), stride, rule, best))
-        return [_hit(b) for b in best]
+    def score_argmax_batch(self, pssms, rule=RULE_AVX2, strands=capi.STRAND_DIRECT):
+        """Many motifs over this sequence (the lightmotif-cli job loop) -> best hit per entry (None for
+        a motif longer than the sequence)."""
+        flat, widths, offs, stride = self._flatten(pssms)
+        n = len(pssms) * (2 if strands == capi.STRAND_BOTH else 1)
+        best = (Hit * n)()
+        status = (C.c_int * n)()
+        self._pli._check(capi.lib().lm_seq_score_argmax_f32_batch_rc(
+            self._pli._ctx, self._h, _ptr(flat), _ptr(widths), _ptr(offs), len(pssms), stride, strands, rule, best, status))
+        return [_hit(b) if status[i] == capi.OK else None for i, b in enumerate(best)]
+
+
+def reverse_complement(pssm):
+    """lm_pssm_reverse_complement: ScoringMatrix::reverse_complement (pwm/mod.rs:566-577), DNA."""
+    p, stride = pad_pssm(pssm, DNA)
+    out = np.zeros_like(p)
+    st = capi.lib().lm_pssm_reverse_complement(_ptr(p), p.shape[0], stride, _ptr(out))
+    if st < 0:
+        raise LightmotifError(st)
+    return out[:, :5].copy()
 
 
 class Scanner:

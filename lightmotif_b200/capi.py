@@ -20,6 +20,7 @@ ERR_INVALID_ARG, ERR_INVALID_SYMBOL, ERR_WRAP, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTE
     -1, -2, -3, -4, -5, -6, -7)
 DNA, PROTEIN = 0, 1
 RULE_GENERIC, RULE_AVX2, RULE_SSE2 = 0, 1, 2
+STRAND_DIRECT, STRAND_REVERSE, STRAND_BOTH = 1, 2, 3
 
 
 class Hit(C.Structure):
@@ -56,7 +57,8 @@ SYMBOLS = [
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
     "lm_seq_score_u8", "lm_seq_score_argmax_f32", "lm_seq_score_argmax_f32_launch",
     "lm_seq_score_argmax_f32_finish", "lm_seq_score_threshold_f32",
-    "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
+    "lm_seq_score_argmax_f32_batch", "lm_seq_score_threshold_f32_batch", "lm_seq_score_argmax_f32_batch_rc",
+    "lm_seq_score_threshold_f32_batch_rc", "lm_pssm_reverse_complement", "lm_argmax_merge", "lm_ctx_result_block", "lm_decode_keys",
     "lm_plan_filter", "lm_plan_filter_protein",
     "lm_comm_init", "lm_comm_init_rank", "lm_comm_connect", "lm_comm_destroy", "lm_comm_last_error",
     "lm_comm_world", "lm_comm_n_local", "lm_comm_ctx", "lm_comm_rank", "lm_comm_shard_from_striped",
@@ -136,6 +138,9 @@ def _declare(L):
     L.lm_seq_score_threshold_f32.argtypes = [vp, vp, vp, sz, sz, sz, sz, C.c_float, hitp, sz, szp]
     L.lm_seq_score_argmax_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, hitp]
     L.lm_seq_score_threshold_f32_batch.argtypes = [vp, vp, vp, vp, vp, sz, sz, vp, hitp, sz, vp]
+    L.lm_seq_score_argmax_f32_batch_rc.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, i, hitp, vp]
+    L.lm_seq_score_threshold_f32_batch_rc.argtypes = [vp, vp, vp, vp, vp, sz, sz, i, vp, hitp, sz, vp]
+    L.lm_pssm_reverse_complement.argtypes = [vp, sz, sz, vp]
     L.lm_argmax_merge.argtypes = [cwp, sz, vp, C.c_float, C.c_uint64, i, hitp]
     L.lm_ctx_result_block.argtypes = [vp, i]
     L.lm_ctx_result_block.restype = vp

@@ -185,6 +185,7 @@ int upload_table(lm_ctx* ctx, int alphabet, const void* pssm, size_t m, size_t s
   std::vector<uint8_t> key = matrix_key(is_u8 ? 2 : 1, alphabet, pssm, m, stride, is_u8 ? 1 : 4);
   if (key == ctx->table_key && ctx->d_table.p) return LM_OK;  // already resident
   ctx->table_key.clear();
+  ctx->batch_staged = false;  // d_table is about to hold this matrix instead of a batch's tables
   const size_t bytes = (size_t)table_mpad(m) * table_kp(alphabet) * 4;
   LM_CHECK(ensure_pinned(ctx, bytes));
   LM_CHECK(ensure(ctx, ctx->d_table, bytes));
@@ -448,6 +449,7 @@ void lm_ctx_destroy(lm_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits, &ctx->d_class})
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  free_batch_cache(ctx->batch);
   for (auto& sl : ctx->slots) {
     if (sl.ev0) cudaEventDestroy(sl.ev0);
     if (sl.ev1) cudaEventDestroy(sl.ev1);
@@ -1237,10 +1239,14 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
   return fetch_hits(ctx, hits, cap, count, SYNC_SMALL_OFF);
 }
 
-// ---- many motifs over one resident sequence (the lightmotif-cli job loop).  Every motif is
-// planned on the host; motifs with a profitable filter run the filter + recheck kernel, the others
-// the exact kernel.  All kernels of the batch are enqueued back to back -- each with its own 512-byte
-// result block and its own tables -- and the host synchronises ONCE at the end.
+}  // extern "C"
+
+// ---- many motifs over one resident sequence (the lightmotif-cli job loop, main.rs:540-562).  Every
+// motif is planned on the host (in parallel; the plans are cached per motif set); motifs whose
+// filters share a kernel instance (look-ups per position, single / paired) are swept over the
+// sequence by ONE launch (work item = (motif, tile), tables travel with the tiles), the running
+// maxima of an argmax batch are seeded by ONE multi-motif exact launch over the first rows, motifs
+// without a profitable filter run the exact kernel; the host synchronises ONCE at the end.
 namespace {
 
 struct BatchItem {
@@ -1248,152 +1254,354 @@ struct BatchItem {
   bool pruned = false;
   PrunePlan plan;
   size_t tab16_off = 0, tab8_off = 0;  // byte offsets into the staged table buffer
+  int group = -1;
+};
+struct BatchGroup {
+  int r = 0, pair = 0, m_max = 0;
+  std::vector<uint32_t> motifs;
+  size_t desc_off = 0;  // byte offset of the group's BatchMotif array in the staged buffer
 };
 
 constexpr size_t BATCH_BLOCK = 512;  // bytes of device scratch per motif (SmallBlock layout)
 
-// plan every motif and stage all tables with one H2D copy; returns device base pointers
-int batch_stage(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths, const uint64_t* offsets,
-                size_t n_motifs, size_t pssm_stride, bool argmax_mode, const float* thresholds, size_t n_rows,
-                std::vector<BatchItem>& items, size_t* max_m_out) {
+// reverse complement of a DNA matrix: rows reversed, columns A<->T, C<->G (pwm/mod.rs:566-577;
+// symbol order A, C, T, G, N: abc.rs:113-135)
+void reverse_complement(const float* p, size_t m, size_t stride, float* out) {
+  static const int comp[5] = {2, 3, 0, 1, 4};
+  for (size_t j = 0; j < m; ++j)
+    for (int c = 0; c < 5; ++c) out[j * stride + c] = p[(m - 1 - j) * stride + comp[c]];
+}
+
+}  // namespace
+
+// host-side state of the batch calls (one per context): the last motif set, planned and staged
+struct lm_batch_cache {
+  std::vector<uint8_t> key;
+  std::vector<float> mats;  // the matrices scanned (direct and / or reverse complement), DenseMatrix layout
+  std::vector<uint64_t> offs;
+  std::vector<uint32_t> widths;
+  std::vector<BatchItem> items;
+  std::vector<BatchGroup> groups;
+  size_t table_bytes = 0, total_bytes = 0, toff_off = 0, mpad_off = 0, max_m = 0;
+};
+
+namespace {
+
+// plan every motif (cached), lay out + upload tables, per-group descriptor arrays and the
+// multi-motif kernel's offset arrays.  Descriptors carry pointers into d_out (result blocks) /
+// d_hits, so they are rebuilt whenever those move or the thresholds change.
+int batch_prepare(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths, const uint64_t* offsets,
+                  size_t n_in, size_t pssm_stride, int strands, bool argmax_mode, const float* thresholds, size_t cap,
+                  lm_batch_cache** out) {
+  if (!ctx->batch) ctx->batch = new (std::nothrow) lm_batch_cache();
+  if (!ctx->batch) return LM_ERR_OOM;
+  lm_batch_cache& B = *ctx->batch;
   const int alphabet = seq->alphabet;
   const int kp = table_kp(alphabet);
-  items.assign(n_motifs, BatchItem());
-  size_t bytes = 0, max_m = 0;
-  const double npos = (double)n_rows * 32.0;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    items[q].m = widths[q];
-    if (widths[q] == 0) return LM_ERR_INVALID_ARG;
-  }
-  // planning is ~0.5 ms of host work per motif: spread it over the host cores
-  if (ctx->opt_prune && alphabet == LM_DNA && n_rows > 16384) {
-    const int opt_prune = ctx->opt_prune, force_r = ctx->opt_filter_rows, force_mode = ctx->opt_filter_mode;
-    const size_t length = seq->length;
-    auto plan_range = [&](size_t q0, size_t q1) {
-      for (size_t q = q0; q < q1; ++q) {
-        BatchItem& it = items[q];
-        if (length < it.m) continue;
-        const float* p = pssms + offsets[q];
-        it.plan = argmax_mode ? plan_prune(p, it.m, pssm_stride, estimate_max_score(p, it.m, pssm_stride, npos), true,
-                                           npos, force_r, force_mode)
-                              : plan_prune(p, it.m, pssm_stride, (double)thresholds[q], false, npos, force_r, force_mode);
-        if (opt_prune == 2 && it.plan.r > 0) it.plan.ok = true;
-        it.pruned = it.plan.ok;
+  const size_t k = (size_t)alphabet_k(alphabet);
+  const size_t n_rows = seq->rows;
+  const bool both = strands == 3, rev_only = strands == 2;
+  const size_t n = n_in * (both ? 2 : 1);
+  // ---- key: everything the plans depend on
+  std::vector<uint8_t> key;
+  {
+    uint64_t hdr[8] = {(uint64_t)alphabet, n_in, (uint64_t)strands, argmax_mode ? 1u : 0u, (uint64_t)ctx->opt_prune,
+                       (uint64_t)ctx->opt_filter_rows, (uint64_t)ctx->opt_filter_mode,
+                       (uint64_t)(63 - __builtin_clzll((unsigned long long)std::max<size_t>(n_rows, 1)))};
+    key.insert(key.end(), (const uint8_t*)hdr, (const uint8_t*)hdr + sizeof(hdr));
+    key.insert(key.end(), (const uint8_t*)widths, (const uint8_t*)(widths + n_in));
+    for (size_t q = 0; q < n_in; ++q)
+      for (size_t j = 0; j < widths[q]; ++j) {
+        const uint8_t* row = (const uint8_t*)(pssms + offsets[q] + j * pssm_stride);
+        key.insert(key.end(), row, row + k * 4);
       }
-    };
-    unsigned hw = std::thread::hardware_concurrency();
-    const size_t n_threads = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, n_motifs / 8}));
-    if (n_threads <= 1) {
-      plan_range(0, n_motifs);
-    } else {
-      std::vector<std::thread> pool;
-      for (size_t t = 0; t < n_threads; ++t)
-        pool.emplace_back(plan_range, n_motifs * t / n_threads, n_motifs * (t + 1) / n_threads);
-      for (auto& th : pool) th.join();
+    if (!argmax_mode) key.insert(key.end(), (const uint8_t*)thresholds, (const uint8_t*)(thresholds + n_in));
+  }
+  if (key != B.key) {
+    B.key.clear();
+    ctx->batch_staged = false;
+    // ---- the matrices to scan: direct, reverse complement, or both (motif i -> entries 2i, 2i + 1)
+    B.widths.assign(n, 0);
+    B.offs.assign(n, 0);
+    size_t total_rows = 0;
+    for (size_t q = 0; q < n; ++q) {
+      const size_t src = both ? q / 2 : q;
+      if (widths[src] == 0) return LM_ERR_INVALID_ARG;
+      B.widths[q] = widths[src];
+      B.offs[q] = total_rows * pssm_stride;
+      total_rows += widths[src];
     }
+    B.mats.assign(total_rows * pssm_stride, 0.f);
+    for (size_t q = 0; q < n; ++q) {
+      const size_t src = both ? q / 2 : q;
+      const bool rc = rev_only || (both && (q & 1));
+      const float* p = pssms + offsets[src];
+      float* dst = B.mats.data() + B.offs[q];
+      if (rc) reverse_complement(p, widths[src], pssm_stride, dst);
+      else
+        for (size_t j = 0; j < widths[src]; ++j) std::memcpy(dst + j * pssm_stride, p + j * pssm_stride, k * 4);
+    }
+    // ---- plans (~0.3 ms of host work per motif: spread over the host cores)
+    B.items.assign(n, BatchItem());
+    const double npos = (double)n_rows * 32.0;
+    for (size_t q = 0; q < n; ++q) B.items[q].m = B.widths[q];
+    if (ctx->opt_prune && alphabet == LM_DNA && n_rows > 16384) {
+      const int opt_prune = ctx->opt_prune, force_r = ctx->opt_filter_rows, force_mode = ctx->opt_filter_mode;
+      const size_t length = seq->length;
+      auto plan_range = [&](size_t q0, size_t q1) {
+        for (size_t q = q0; q < q1; ++q) {
+          BatchItem& it = B.items[q];
+          if (length < it.m || it.m > 64) continue;
+          const float* p = B.mats.data() + B.offs[q];
+          const float thr = argmax_mode ? 0.f : thresholds[both ? q / 2 : q];
+          it.plan = argmax_mode ? plan_prune(p, it.m, pssm_stride, estimate_max_score(p, it.m, pssm_stride, npos), true,
+                                             npos, force_r, force_mode)
+                                : plan_prune(p, it.m, pssm_stride, (double)thr, false, npos, force_r, force_mode);
+          if (opt_prune == 2 && it.plan.r > 0) it.plan.ok = true;
+          it.pruned = it.plan.ok;
+        }
+      };
+      unsigned hw = std::thread::hardware_concurrency();
+      const size_t n_threads = std::max<size_t>(1, std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)32, n / 8}));
+      if (n_threads <= 1) {
+        plan_range(0, n);
+      } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(plan_range, n * t / n_threads, n * (t + 1) / n_threads);
+        for (auto& th : pool) th.join();
+      }
+    }
+    // ---- groups of motifs that share a kernel instance; layout of the staged buffer
+    B.groups.clear();
+    size_t bytes = 0;
+    B.max_m = 0;
+    for (size_t q = 0; q < n; ++q) {
+      BatchItem& it = B.items[q];
+      B.max_m = std::max(B.max_m, it.m);
+      it.tab16_off = bytes;
+      bytes += (size_t)table_mpad(it.m) * kp * 4;
+      it.tab8_off = bytes;
+      if (it.pruned) {
+        bytes += (size_t)table_mpad(it.m) * 8 * 4;
+        int g = -1;
+        for (size_t i = 0; i < B.groups.size(); ++i)
+          if (B.groups[i].r == it.plan.r && B.groups[i].pair == it.plan.pair) g = (int)i;
+        if (g < 0) {
+          B.groups.push_back(BatchGroup());
+          g = (int)B.groups.size() - 1;
+          B.groups[g].r = it.plan.r;
+          B.groups[g].pair = it.plan.pair;
+        }
+        B.groups[g].motifs.push_back((uint32_t)q);
+        B.groups[g].m_max = std::max(B.groups[g].m_max, (int)it.m);
+        it.group = g;
+      }
+    }
+    B.table_bytes = bytes = (bytes + 255) & ~(size_t)255;
+    B.toff_off = bytes;
+    bytes += n * 8;
+    B.mpad_off = bytes;
+    bytes = (bytes + n * 4 + 255) & ~(size_t)255;
+    for (auto& g : B.groups) {
+      g.desc_off = bytes;
+      bytes += g.motifs.size() * sizeof(BatchMotif);
+    }
+    B.total_bytes = bytes;
+    B.key.swap(key);
   }
-  for (size_t q = 0; q < n_motifs; ++q) {
-    BatchItem& it = items[q];
-    max_m = std::max(max_m, it.m);
-    it.tab16_off = bytes;
-    bytes += (size_t)table_mpad(it.m) * kp * 4;
-    it.tab8_off = bytes;
-    if (it.pruned) bytes += (size_t)table_mpad(it.m) * 8 * 4;
-  }
-  *max_m_out = max_m;
-  LM_CHECK(ensure_pinned(ctx, bytes + 64));
-  LM_CHECK(ensure(ctx, ctx->d_table, bytes + 64));
+  // ---- (re)build the staged image: tables once per motif set, descriptors every call
+  LM_CHECK(ensure_pinned(ctx, B.total_bytes + 64));
+  LM_CHECK(ensure(ctx, ctx->d_table, B.total_bytes + 64));
+  LM_CHECK(ensure(ctx, ctx->d_out, n * BATCH_BLOCK + 1024));
+  if (!argmax_mode) LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(n * cap, 1) * sizeof(lm_hit)));
   ctx->table_key.clear();  // d_table now holds the batch, not a single matrix
+  ctx->table8_key.clear();
   uint8_t* h = (uint8_t*)ctx->h_pin;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    const BatchItem& it = items[q];
-    const float* p = pssms + offsets[q];
-    build_table_f32(alphabet, p, it.m, pssm_stride, (uint32_t*)(h + it.tab16_off));
-    if (it.pruned) {
-      float* t8 = (float*)(h + it.tab8_off);
-      std::memset(t8, 0, (size_t)table_mpad(it.m) * 8 * 4);
-      for (size_t j = 0; j < it.m; ++j)
-        for (int a = 0; a < 5; ++a) t8[j * 8 + a] = p[j * pssm_stride + a];
+  uint8_t* dbase = (uint8_t*)ctx->d_table.p;
+  const size_t first = ctx->batch_staged ? B.table_bytes : 0;  // the tables are still on the device
+  if (!ctx->batch_staged) {
+    for (size_t q = 0; q < n; ++q) {
+      const BatchItem& it = B.items[q];
+      const float* p = B.mats.data() + B.offs[q];
+      build_table_f32(alphabet, p, it.m, pssm_stride, (uint32_t*)(h + it.tab16_off));
+      if (it.pruned) {
+        float* t8 = (float*)(h + it.tab8_off);
+        std::memset(t8, 0, (size_t)table_mpad(it.m) * 8 * 4);
+        for (size_t j = 0; j < it.m; ++j)
+          for (int a = 0; a < 5; ++a) t8[j * 8 + a] = p[j * pssm_stride + a];
+      }
     }
   }
-  LM_TRY(cudaMemcpyAsync(ctx->d_table.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t* toff = (uint64_t*)(h + B.toff_off);
+  int* mpads = (int*)(h + B.mpad_off);
+  for (size_t q = 0; q < n; ++q) {
+    toff[q] = B.items[q].tab16_off / 4;
+    mpads[q] = table_mpad(B.items[q].m);
+  }
+  for (const auto& g : B.groups) {
+    BatchMotif* bm = (BatchMotif*)(h + g.desc_off);
+    for (size_t i = 0; i < g.motifs.size(); ++i) {
+      const uint32_t q = g.motifs[i];
+      const BatchItem& it = B.items[q];
+      BatchMotif& M = bm[i];
+      M = BatchMotif();
+      for (int t = 0; t < 16; ++t) { M.tab[t] = it.plan.tab_lo[t]; M.tab[16 + t] = it.plan.tab_hi[t]; }
+      M.c0 = it.plan.c0; M.delta = it.plan.delta; M.eps = it.plan.eps;
+      M.m = it.plan.m; M.j0 = it.plan.j0; M.smax = it.plan.smax; M.pair_mul = it.plan.pair_mul;
+      M.table = (const float*)(dbase + it.tab8_off);
+      M.block = (unsigned long long*)((uint8_t*)ctx->d_out.p + (size_t)q * BATCH_BLOCK);
+      if (!argmax_mode) {
+        M.hits = (lm_hit*)ctx->d_hits.p + (size_t)q * cap;
+        M.cap = cap;
+        M.thr = thresholds[both ? q / 2 : q];
+      }
+    }
+  }
+  LM_TRY(cudaMemcpyAsync(dbase + first, h + first, B.total_bytes - first, cudaMemcpyHostToDevice, ctx->stream));
+  // (the pinned image is rewritten by the next call: it must have left the host before we return --
+  // every batch call ends with a stream synchronisation)
+  ctx->batch_staged = true;
+  *out = &B;
+  return LM_OK;
+}
+
+// enqueue the scans of a prepared batch.  n_rows > 0, motifs longer than the sequence are skipped.
+int batch_launch(lm_ctx* ctx, const lm_seq* seq, lm_batch_cache& B, bool argmax_mode, const float* thresholds, int strands,
+                 size_t cap, uint64_t* n_pruned_out, uint64_t* launches_out) {
+  const int alphabet = seq->alphabet;
+  const size_t n = B.items.size(), n_rows = seq->rows;
+  const int sms = std::max(1, ctx->sm_count - ctx->opt_reserve_sms);
+  uint8_t* dbase = (uint8_t*)ctx->d_table.p;
+  uint8_t* blocks = (uint8_t*)ctx->d_out.p;
+  uint8_t* scratch = blocks + n * BATCH_BLOCK;  // launch-level counters of the grouped launches
+  uint64_t launches = 0, n_pruned = 0;
+  LM_TRY(cudaMemsetAsync(blocks, 0, n * BATCH_BLOCK + 1024, ctx->stream));
+  // rows scored exactly first to seed the running maxima of the filtered argmax scans
+  const size_t boot = argmax_mode ? std::min<size_t>(n_rows, 16384) : 0;
+  bool any_pruned = false;
+  for (const auto& it : B.items) any_pruned = any_pruned || (it.pruned && seq->length >= it.m);
+  if (argmax_mode && any_pruned && boot) {
+    // ONE multi-motif exact launch over rows [0, boot): tile resident in shared memory, loop over the motifs
+    ScoreArgs a;
+    a.seq = seq->data;
+    a.avail_rows = seq->alloc_rows;
+    a.row_begin = 0;
+    a.row_end = boot;
+    a.pad_sym = pad_symbol(alphabet);
+    a.tables = (const uint32_t*)dbase;
+    a.table_off = (const uint64_t*)(dbase + B.toff_off);
+    a.m_pads = (const int*)(dbase + B.mpad_off);
+    a.m_pad = table_mpad(B.max_m);
+    a.n_motifs = (int)n;
+    a.colkeys = (unsigned long long*)blocks;
+    a.colkeys_stride = BATCH_BLOCK / 8;
+    a.first_cell = (uint32_t*)(blocks + 256);
+    a.first_cell_stride = BATCH_BLOCK / 4;
+    LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, sms, ctx->stream));
+    ++launches;
+  }
+  // ONE launch per group of filtered motifs
+  size_t gi = 0;
+  for (const auto& g : B.groups) {
+    PruneArgs pa;
+    pa.seq = seq->data;
+    pa.avail_rows = seq->alloc_rows;
+    pa.row_begin = 0;
+    pa.row_first = boot;
+    pa.row_end = n_rows;
+    pa.pad_sym = pad_symbol(alphabet);
+    pa.plan.r = g.r;
+    pa.plan.pair = g.pair;
+    pa.batch = (const BatchMotif*)(dbase + g.desc_off);
+    pa.n_batch = (uint32_t)g.motifs.size();
+    pa.m_max = g.m_max;
+    pa.stats = (unsigned long long*)(scratch + (gi % 16) * 64);
+    if (n_rows > boot) {
+      LM_TRY(launch_prune(!argmax_mode, pa, sms, ctx->stream));
+      ++launches;
+    }
+    n_pruned += g.motifs.size();
+    ++gi;
+  }
+  // motifs without a profitable filter: the exact kernel over every row
+  for (size_t q = 0; q < n; ++q) {
+    const BatchItem& it = B.items[q];
+    if (it.pruned || seq->length < it.m) continue;
+    uint8_t* block = blocks + q * BATCH_BLOCK;
+    ScoreArgs a;
+    a.seq = seq->data;
+    a.avail_rows = seq->alloc_rows;
+    a.row_begin = 0;
+    a.row_end = n_rows;
+    a.pad_sym = pad_symbol(alphabet);
+    a.tables = (const uint32_t*)(dbase + it.tab16_off);
+    a.m_pad = table_mpad(it.m);
+    a.n_motifs = 1;
+    a.colkeys = (unsigned long long*)block;
+    a.first_cell = (uint32_t*)(block + 256);
+    if (argmax_mode) {
+      LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, sms, ctx->stream));
+      ++launches;
+    } else {
+      a.count = (unsigned long long*)(block + 264);
+      const float thr = thresholds[strands == 3 ? q / 2 : q];
+      std::memcpy(&a.thr_bits, &thr, 4);
+      a.hits = (lm_hit*)ctx->d_hits.p + q * cap;
+      a.cap = cap;
+      LM_TRY(launch_score(alphabet, MODE_THRESHOLD, false, a, sms, ctx->stream));
+      ++launches;
+    }
+  }
+  *n_pruned_out = n_pruned;
+  *launches_out = launches;
   return LM_OK;
 }
 
 }  // namespace
 
-int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
-                                  const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int rule,
-                                  lm_hit* best) {
+void free_batch_cache(lm_batch_cache* b) { delete b; }
+
+extern "C" {
+
+int lm_seq_score_argmax_f32_batch_rc(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                     const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int strands, int rule,
+                                     lm_hit* best, int* status) {
   LM_CHECK(bind(ctx));
-  if (!seq || !pssms || !widths || !offsets || !best || pssm_stride < (size_t)alphabet_k(seq->alphabet))
+  if (!seq || !pssms || !widths || !offsets || !best || pssm_stride < (size_t)alphabet_k(seq->alphabet) ||
+      strands < 1 || strands > 3 || (strands != 1 && seq->alphabet != LM_DNA))
     return LM_ERR_INVALID_ARG;
   if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
   if (n_motifs == 0) return LM_OK;
   if (n_motifs > 65536) return LM_ERR_UNSUPPORTED;
-  const int alphabet = seq->alphabet;
-  const size_t n_rows = seq->rows;
-  std::vector<BatchItem> items;
+  const size_t n = n_motifs * (strands == 3 ? 2 : 1);
   size_t max_m = 0;
   for (size_t q = 0; q < n_motifs; ++q) max_m = std::max<size_t>(max_m, widths[q]);
   int st = check_score_args(max_m ? max_m : 1, seq->rows, seq->wrap, std::max(seq->length, max_m), 0, seq->rows);
   if (st < 0) return st;
-  LM_CHECK(limits_ok(alphabet, max_m));
-  LM_CHECK(batch_stage(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, true, nullptr, n_rows, items, &max_m));
-  LM_CHECK(ensure(ctx, ctx->d_out, n_motifs * BATCH_BLOCK));
-  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, n_motifs * BATCH_BLOCK, ctx->stream));
-  const int sms = std::max(1, ctx->sm_count - ctx->opt_reserve_sms);
-  // rows scored exactly first to seed each filtered scan's running maximum
-  const size_t boot = std::min<size_t>(ctx->opt_boot_rows, std::max<size_t>(8192, n_rows / 32));
-  timer_begin(ctx);
-  uint64_t n_pruned = 0, launches = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    const BatchItem& it = items[q];
-    if (seq->length < it.m) continue;  // nothing to score: best[q] stays zeroed
-    uint8_t* block = (uint8_t*)ctx->d_out.p + q * BATCH_BLOCK;
-    ScoreArgs a;
-    a.seq = seq->data;
-    a.avail_rows = seq->alloc_rows;
-    a.row_begin = 0;
-    a.row_end = it.pruned ? std::min(boot, n_rows) : n_rows;
-    a.pad_sym = pad_symbol(alphabet);
-    a.tables = (const uint32_t*)((uint8_t*)ctx->d_table.p + it.tab16_off);
-    a.m_pad = table_mpad(it.m);
-    a.n_motifs = 1;
-    a.colkeys = (unsigned long long*)block;
-    a.first_cell = (uint32_t*)(block + 256);
-    LM_TRY(launch_score(alphabet, MODE_ARGMAX, false, a, sms, ctx->stream));
-    ++launches;
-    if (it.pruned && n_rows > boot) {
-      PruneArgs pa;
-      pa.seq = seq->data;
-      pa.avail_rows = seq->alloc_rows;
-      pa.row_begin = 0;
-      pa.row_first = boot;
-      pa.row_end = n_rows;
-      pa.pad_sym = pad_symbol(alphabet);
-      pa.table = (const float*)((uint8_t*)ctx->d_table.p + it.tab8_off);
-      pa.plan = it.plan;
-      pa.colkeys = (unsigned long long*)block;
-      pa.stats = (unsigned long long*)(block + 272);
-      LM_TRY(launch_prune(false, pa, sms, ctx->stream));
-      ++launches;
-      ++n_pruned;
-    }
+  LM_CHECK(limits_ok(seq->alphabet, max_m));
+  for (size_t q = 0; q < n; ++q) {
+    std::memset(&best[q], 0, sizeof(lm_hit));
+    if (status) status[q] = LM_EMPTY;
   }
+  if (st == LM_EMPTY) return LM_OK;  // no rows: every motif is "None"
+  lm_batch_cache* B = nullptr;
+  LM_CHECK(batch_prepare(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, strands, true, nullptr, 0, &B));
+  uint64_t n_pruned = 0, launches = 0;
+  timer_begin(ctx);
+  LM_CHECK(batch_launch(ctx, seq, *B, true, nullptr, strands, 0, &n_pruned, &launches));
   timer_end(ctx);
   ctx->launches += launches;
-  std::vector<uint8_t> blocks(n_motifs * BATCH_BLOCK);
+  std::vector<uint8_t> blocks(n * BATCH_BLOCK);
   LM_TRY(cudaMemcpyAsync(blocks.data(), ctx->d_out.p, blocks.size(), cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   uint64_t cand = 0, over = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
+  for (size_t q = 0; q < n; ++q) {
     const SmallBlock* sb = (const SmallBlock*)(blocks.data() + q * BATCH_BLOCK);
+    if (seq->length < B->items[q].m) continue;  // LM_EMPTY: the reference's scores.resize(0, 0) -> argmax None
     lm_colwin cw[32];
     decode_colwins(sb->ck.keys, false, cw);
-    std::memset(&best[q], 0, sizeof(lm_hit));
-    if (seq->length < widths[q]) continue;
-    apply_rule(cw, bits_to_score(sb->ck.first_cell, false), rule, false, seq->rows, 0, &best[q]);
+    const int r = apply_rule(cw, bits_to_score(sb->ck.first_cell, false), rule, false, seq->rows, 0, &best[q]);
+    if (status) status[q] = r;
     cand += sb->stats[0];
     over += sb->stats[1];
   }
@@ -1404,98 +1612,78 @@ int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* p
   return LM_OK;
 }
 
-int lm_seq_score_threshold_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
-                                     const uint64_t* offsets, size_t n_motifs, size_t pssm_stride,
-                                     const float* thresholds, lm_hit* hits, size_t cap, size_t* counts) {
+int lm_seq_score_argmax_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                  const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int rule,
+                                  lm_hit* best) {
+  return lm_seq_score_argmax_f32_batch_rc(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, LM_STRAND_DIRECT, rule,
+                                          best, nullptr);
+}
+
+int lm_seq_score_threshold_f32_batch_rc(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                        const uint64_t* offsets, size_t n_motifs, size_t pssm_stride, int strands,
+                                        const float* thresholds, lm_hit* hits, size_t cap, size_t* counts) {
   LM_CHECK(bind(ctx));
   if (!seq || !pssms || !widths || !offsets || !thresholds || !counts || (cap && !hits) ||
-      pssm_stride < (size_t)alphabet_k(seq->alphabet))
+      pssm_stride < (size_t)alphabet_k(seq->alphabet) || strands < 1 || strands > 3 ||
+      (strands != 1 && seq->alphabet != LM_DNA))
     return LM_ERR_INVALID_ARG;
   if (seq->device != ctx->device) return LM_ERR_INVALID_ARG;
-  for (size_t q = 0; q < n_motifs; ++q) counts[q] = 0;
+  const size_t n = n_motifs * (strands == 3 ? 2 : 1);
+  for (size_t q = 0; q < n; ++q) counts[q] = 0;
   if (n_motifs == 0) return LM_OK;
   if (n_motifs > 65536) return LM_ERR_UNSUPPORTED;
-  const int alphabet = seq->alphabet;
-  const size_t n_rows = seq->rows;
   size_t max_m = 0;
   for (size_t q = 0; q < n_motifs; ++q) max_m = std::max<size_t>(max_m, widths[q]);
   int st = check_score_args(max_m ? max_m : 1, seq->rows, seq->wrap, std::max(seq->length, max_m), 0, seq->rows);
   if (st < 0) return st;
-  LM_CHECK(limits_ok(alphabet, max_m));
-  std::vector<BatchItem> items;
-  LM_CHECK(batch_stage(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, false, thresholds, n_rows, items, &max_m));
-  LM_CHECK(ensure(ctx, ctx->d_out, n_motifs * BATCH_BLOCK));
-  LM_CHECK(ensure(ctx, ctx->d_hits, std::max<size_t>(n_motifs * cap, 1) * sizeof(lm_hit)));
-  LM_TRY(cudaMemsetAsync(ctx->d_out.p, 0, n_motifs * BATCH_BLOCK, ctx->stream));
-  const int sms = std::max(1, ctx->sm_count - ctx->opt_reserve_sms);
-  timer_begin(ctx);
+  if (st == LM_EMPTY) return LM_OK;
+  LM_CHECK(limits_ok(seq->alphabet, max_m));
+  lm_batch_cache* B = nullptr;
+  LM_CHECK(batch_prepare(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, strands, false, thresholds, cap, &B));
   uint64_t n_pruned = 0, launches = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
-    const BatchItem& it = items[q];
-    if (seq->length < it.m) continue;
-    uint8_t* block = (uint8_t*)ctx->d_out.p + q * BATCH_BLOCK;
-    lm_hit* d_hits = (lm_hit*)ctx->d_hits.p + q * cap;
-    if (it.pruned) {
-      PruneArgs pa;
-      pa.seq = seq->data;
-      pa.avail_rows = seq->alloc_rows;
-      pa.row_begin = 0;
-      pa.row_first = 0;
-      pa.row_end = n_rows;
-      pa.pad_sym = pad_symbol(alphabet);
-      pa.table = (const float*)((uint8_t*)ctx->d_table.p + it.tab8_off);
-      pa.plan = it.plan;
-      pa.thr = thresholds[q];
-      pa.hits = d_hits;
-      pa.cap = cap;
-      pa.count = (unsigned long long*)(block + 264);
-      pa.stats = (unsigned long long*)(block + 272);
-      LM_TRY(launch_prune(true, pa, sms, ctx->stream));
-      ++n_pruned;
-    } else {
-      ScoreArgs a;
-      a.seq = seq->data;
-      a.avail_rows = seq->alloc_rows;
-      a.row_begin = 0;
-      a.row_end = n_rows;
-      a.pad_sym = pad_symbol(alphabet);
-      a.tables = (const uint32_t*)((uint8_t*)ctx->d_table.p + it.tab16_off);
-      a.m_pad = table_mpad(it.m);
-      a.n_motifs = 1;
-      a.colkeys = (unsigned long long*)block;
-      a.first_cell = (uint32_t*)(block + 256);
-      a.count = (unsigned long long*)(block + 264);
-      std::memcpy(&a.thr_bits, &thresholds[q], 4);
-      a.hits = d_hits;
-      a.cap = cap;
-      LM_TRY(launch_score(alphabet, MODE_THRESHOLD, false, a, sms, ctx->stream));
-    }
-    ++launches;
-  }
+  timer_begin(ctx);
+  LM_CHECK(batch_launch(ctx, seq, *B, false, thresholds, strands, cap, &n_pruned, &launches));
   timer_end(ctx);
   ctx->launches += launches;
-  std::vector<uint8_t> blocks(n_motifs * BATCH_BLOCK);
+  std::vector<uint8_t> blocks(n * BATCH_BLOCK);
   LM_TRY(cudaMemcpyAsync(blocks.data(), ctx->d_out.p, blocks.size(), cudaMemcpyDeviceToHost, ctx->stream));
   LM_TRY(cudaStreamSynchronize(ctx->stream));
   bool overflow = false;
   uint64_t cand = 0, over = 0;
-  for (size_t q = 0; q < n_motifs; ++q) {
+  size_t max_n = 0;
+  for (size_t q = 0; q < n; ++q) {
     const SmallBlock* sb = (const SmallBlock*)(blocks.data() + q * BATCH_BLOCK);
     counts[q] = (size_t)sb->count;
     cand += sb->stats[0];
     over += sb->stats[1];
-    const size_t n = std::min<size_t>(counts[q], cap);
     overflow = overflow || counts[q] > cap;
-    if (n) LM_TRY(cudaMemcpyAsync(hits + q * cap, (lm_hit*)ctx->d_hits.p + q * cap, n * sizeof(lm_hit),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    max_n = std::max(max_n, std::min<size_t>(counts[q], cap));
   }
-  LM_TRY(cudaStreamSynchronize(ctx->stream));
-  for (size_t q = 0; q < n_motifs; ++q) sort_hits(hits + q * cap, std::min<size_t>(counts[q], cap));
+  // all hit lists with ONE strided copy (rows = motifs, width = the longest list)
+  if (max_n) {
+    LM_TRY(cudaMemcpy2DAsync(hits, cap * sizeof(lm_hit), ctx->d_hits.p, cap * sizeof(lm_hit), max_n * sizeof(lm_hit), n,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    LM_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  for (size_t q = 0; q < n; ++q) sort_hits(hits + q * cap, std::min<size_t>(counts[q], cap));
   ctx->stats[0] = cand;
   ctx->stats[1] = over;
   ctx->stats[2] = n_pruned;
   ctx->stats[3] = 0;
   return overflow ? LM_ERR_OVERFLOW : LM_OK;
+}
+
+int lm_seq_score_threshold_f32_batch(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint32_t* widths,
+                                     const uint64_t* offsets, size_t n_motifs, size_t pssm_stride,
+                                     const float* thresholds, lm_hit* hits, size_t cap, size_t* counts) {
+  return lm_seq_score_threshold_f32_batch_rc(ctx, seq, pssms, widths, offsets, n_motifs, pssm_stride, LM_STRAND_DIRECT,
+                                             thresholds, hits, cap, counts);
+}
+
+int lm_pssm_reverse_complement(const float* pssm, size_t m, size_t pssm_stride, float* out) {
+  if (!pssm || !out || pssm_stride < 5 || pssm == out) return LM_ERR_INVALID_ARG;
+  reverse_complement(pssm, m, pssm_stride, out);
+  return LM_OK;
 }
 
 int lm_plan_filter(const float* pssm, size_t m, size_t pssm_stride, double threshold, int is_argmax,

@@ -12,6 +12,9 @@
 
 // ------------------------------------------------------------------ context
 
+struct lm_batch_cache;  // capi.cu: the last motif set of the batch calls, planned and staged
+void free_batch_cache(lm_batch_cache* b);
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -59,6 +62,8 @@ struct lm_ctx {
     bool pruned = false;
     int r = 0;
   } slots[LM_SLOTS];
+  lm_batch_cache* batch = nullptr;
+  bool batch_staged = false;                      // d_table still holds that set's tables
   void* h_pin = nullptr;                          // pinned host staging
   size_t h_pin_bytes = 0;
 };

@@ -48,9 +48,6 @@ namespace {
 #endif
 constexpr int PW = LM_PRUNE_PW;         // consumer (filter) warps per CTA
 constexpr int PT = (PW + 1) * 32;       // + one producer warp
-#ifndef LM_PRUNE_G
-#define LM_PRUNE_G LM_PRUNE_PL  // rows per look-up block (operand reuse, accumulator ILP, one test per block)
-#endif
 #ifndef LM_PRUNE_PSLEEP
 #define LM_PRUNE_PSLEEP 50   // ns between the producer's polls of an `empty` barrier
 #endif
@@ -58,17 +55,8 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #define LM_PRUNE_CSLEEP 20   // ns between a consumer warp's polls of a `full` barrier
 #endif
 #ifndef LM_PRUNE_EXP
-#define LM_PRUNE_EXP 0
-#endif
-#ifndef LM_PRUNE_L2PF
-#define LM_PRUNE_L2PF 0      // L2 prefetch distance in grid rounds (0 = off): tile t + L2PF * gridDim.x
-#endif
-#ifndef LM_PRUNE_PROF
-#define LM_PRUNE_PROF 0      // 1: CTAs 0 and 77 print a cycle breakdown of their pipeline (diagnostic builds only)
-#endif
-#ifndef LM_PRUNE_WAIT
-#define LM_PRUNE_WAIT 0      // 0: try_wait + nanosleep back-off, 1: plain try_wait loop, 2: try_wait with suspend hint
-#endif
+#define LM_PRUNE_EXP 0       // experiments (timing only, wrong results): 1 = stream the tiles without filtering,
+#endif                       // 2 = tiles cycle through an L2-resident window, 4 = never leave the fast path
 #ifndef LM_PRUNE_SPT
 #define LM_PRUNE_SPT 8       // slices (one warp's worth of rows) per staged tile
 #endif
@@ -89,35 +77,42 @@ constexpr int PTILE_ROWS = SPT * WARP_ROWS;
 constexpr int CLAIM = PW / SPT > 0 ? PW / SPT : 1;  // consecutive tiles a producer claims per trip to the global counter
 static_assert(NSTAGE * SPT > PW + SPT - 1 || NSTAGE * SPT >= 2 * PW, "ring too shallow for the slices in flight");
 constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
-
-__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity, uint32_t ns) {
-#if LM_PRUNE_WAIT == 1
-  (void)ns;
-  mbar_wait(bar, parity);
-#elif LM_PRUNE_WAIT == 2
-  (void)ns;
-  mbar_wait_hint(bar, parity, 20000u);
-#else
-  mbar_wait_backoff(bar, parity, ns);
-#endif
-}
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
-struct PSmem {
-  uint32_t table_off, ctl_off, queue_off, raw_off, raw_bytes, total;
+// What a consumer warp needs to know about the tile in a stage.  Everything that depends on the
+// MOTIF travels with the tile, so one launch can sweep many motifs over the sequence (work item =
+// (motif, tile)): the filter tables, the filter window, the recheck table (a per-stage copy in
+// shared memory) and the motif's result block.
+struct TileDesc {
+  unsigned long long tile;      // tile index within the motif's sweep; >= num_tiles: end marker
+  unsigned long long* block;    // the motif's result block (keys[32] | first cell | hit count | statistics)
+  lm_hit* hits;                 // threshold mode
+  unsigned long long cap;
+  uint32_t bias4;               // 128 - (quantised threshold), replicated in the 4 byte lanes
+  float thr;                    // the threshold the tile is filtered / rechecked at
+  uint32_t avail, valid;        // rows the copy delivers; rows of the tile inside the scored range
+  uint32_t mq;                  // motif index within the launch
+  int m_pad, j0;
+  uint32_t pair_mul;
+  uint32_t tabs[32];            // filter tables: entries 0..3 of look-up k in tabs[k], 4..7 in tabs[16 + k]
 };
-// pipeline control block: full[s] (TMA landed + descriptor valid) / empty[s] (all consumer warps done)
+// pipeline control block: full[s] (TMA landed + descriptor valid) / empty[s] (all slices of the tile done)
 struct Ctl {
   uint64_t full[NSTAGE], empty[NSTAGE];
-  struct { unsigned long long tile; uint32_t bias4; float thr; uint32_t avail, valid; } desc[NSTAGE];  // avail: rows the copy delivers; valid: rows of the tile inside the scored range
   uint32_t next_slice;      // slices (WARP_ROWS rows of a tile) handed out to the consumer warps so far
-  long long t_issue[NSTAGE];  // LM_PRUNE_PROF: SM clock when the stage's TMA copy was issued
+  uint32_t stage_mq[NSTAGE];  // motif whose recheck table each stage's table slot holds (producer only)
+  TileDesc desc[NSTAGE];
 };
-__host__ __device__ inline PSmem psmem(int m, int tab_stride) {
+struct PSmem {
+  uint32_t table_off, table_bytes, ctl_off, queue_off, raw_off, raw_bytes, total;
+};
+__host__ __device__ inline PSmem psmem(int m_max, int tab_stride) {
   PSmem s;
-  uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);
+  const uint32_t mp = (uint32_t)((m_max + 3) & ~3);
+  const uint32_t tt = PTILE_ROWS + mp;
   s.table_off = 0;
-  s.ctl_off = ((uint32_t)((m + 3) & ~3) * tab_stride * 4 + 127) & ~127u;
+  s.table_bytes = (mp * tab_stride * 4 + 127) & ~127u;  // one recheck table per stage
+  s.ctl_off = NSTAGE * s.table_bytes;
   s.queue_off = (s.ctl_off + (uint32_t)sizeof(Ctl) + 127) & ~127u;
   s.raw_off = s.queue_off + PW * QCAP * 4;
   s.raw_bytes = (tt * 32 + 127) & ~127u;
@@ -134,17 +129,10 @@ __device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t se
 
 // acc + p as `p * one + acc`: an IMAD on the (otherwise idle) FMA pipe instead of an IADD3 on the
 // ALU pipe that the PRMT look-ups saturate.  `one` is a kernel parameter so ptxas cannot fold it.
-#ifndef LM_PRUNE_IMAD
-#define LM_PRUNE_IMAD 1
-#endif
 __device__ __forceinline__ uint32_t add_fma_pipe(uint32_t p, uint32_t one, uint32_t acc) {
-#if LM_PRUNE_IMAD
   uint32_t d;
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(p), "r"(one), "r"(acc));
   return d;
-#else
-  return acc + p;
-#endif
 }
 
 // PRMT selector of a quad (4 symbols, one per byte, each <= 7): a single IDP.2A (FMA pipe)
@@ -158,21 +146,22 @@ __device__ __forceinline__ uint32_t make_sel(uint32_t x) {
 }
 __device__ __constant__ const uint8_t LANE_COL[4] = {0, 2, 1, 3};
 
+// a cell that reaches the threshold: hit record (threshold mode) or per-column winner (argmax mode)
 template <bool THR>
-__device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel_row, uint32_t col) {
+__device__ __forceinline__ void record(const PruneArgs& a, const TileDesc& d, float s, uint32_t rel_row, uint32_t col) {
   if (THR) {
-    unsigned long long slot = atomicAdd(a.count, 1ull);
-    if (slot < a.cap) {
+    unsigned long long slot = atomicAdd(d.block + 33, 1ull);
+    if (slot < d.cap) {
       lm_hit h;
       h.row = rel_row + a.row_add;
       h.col = col;
       h.position = (uint64_t)col * (a.pos_rows ? a.pos_rows : a.row_end - a.row_begin) + h.row;
       h.score = s;
-      a.hits[slot] = h;
+      d.hits[slot] = h;
     }
   } else {
     unsigned long long key = ((unsigned long long)f32_to_key(s) << 32) | rel_row;
-    atomicMax(&a.colkeys[col], key);
+    atomicMax(&d.block[col], key);
   }
 }
 
@@ -180,9 +169,9 @@ __device__ __forceinline__ void record(const PruneArgs& a, float s, uint32_t rel
 // to a multiple of 4 rows with +0.0 (x + 0.0 == x: the chain starts at +0.0 and never yields -0.0).
 __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* tab, int m_pad,
                                              uint32_t row_in_tile, uint32_t col) {
-  // The candidate's warp waits for this chain, and the other warps of the CTA end up waiting for that
-  // warp: keep its latency short.  All symbol loads of a block of 8 motif rows are issued before
-  // the first look-up, all look-ups before the first add; only the adds are sequential (they must be).
+  // The candidate's warp waits for this chain: keep its latency short.  All symbol loads of a block
+  // of 8 motif rows are issued before the first look-up, all look-ups before the first add; only the
+  // adds are sequential (they must be).
   float s = 0.0f;
   const uint8_t* p = rawb + row_in_tile * 32 + col;
   int j = 0;
@@ -210,25 +199,32 @@ __device__ __forceinline__ float exact_score(const uint8_t* rawb, const float* t
 }
 // same from the residues in global memory (protein: the tile holds class codes); rows past the
 // readable extent are the default symbol
-__device__ __forceinline__ float exact_score_global(const PruneArgs& a, const float* tab, int m_pad, uint64_t row,
-                                                    uint32_t col) {
+// (not inlined: it is cold code, and the consumer loop must stay small -- beyond ~40 KB of SASS the
+// warps start to wait for instruction fetches: "no_instruction" rose from 0.4 to 1.0 in ncu)
+__device__ __noinline__ float exact_score_global(const uint8_t* seq_exact, uint64_t avail_rows, uint32_t pad_sym,
+                                                 const float* tab, int tab_stride, int m_pad, uint64_t row,
+                                                 uint32_t col) {
   float s = 0.0f;
   for (int j = 0; j < m_pad; ++j) {
     const uint64_t r = row + j;
-    const uint32_t sym = r < a.avail_rows ? a.seq_exact[r * 32 + col] : a.pad_sym;
-    s = __fadd_rn(s, tab[j * a.tab_stride + sym]);
+    const uint32_t sym = r < avail_rows ? seq_exact[r * 32 + col] : pad_sym;
+    s = __fadd_rn(s, tab[j * tab_stride + sym]);
   }
   return s;
 }
 
-template <int R, bool PAIR, bool THR>
+// BATCH = false: one motif, whose filter parameters are kernel arguments (uniform registers) and whose
+// tables are loaded into registers once -- the instance the single-motif scans (and the headline
+// benchmark) run; BATCH = true: the parameters travel with the tiles.  The look-up loop is identical,
+// but it needs every register ptxas has (72 at 3 CTAs/SM): two more live values and it either spills
+// or gives up interleaving the selector loads with the look-ups (measured: -10 %).
+template <int R, bool PAIR, bool THR, bool BATCH>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int m = a.plan.m;
-  const PSmem S = psmem(m, a.tab_stride);
-  const uint32_t tt = PTILE_ROWS + ((m + 3) & ~3);  // rows staged per tile (tile + halo)
-  float* tab = reinterpret_cast<float*>(smem + S.table_off);
+  const PSmem S = psmem(a.m_max, a.tab_stride);
+  const uint32_t halo = (uint32_t)((a.m_max + 3) & ~3);
+  const uint32_t tt = PTILE_ROWS + halo;  // rows staged per tile (tile + halo of the widest motif)
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + S.ctl_off);
   uint8_t* raw = smem + S.raw_off;
 
@@ -238,18 +234,31 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       mbar_init(&ctl->empty[s], SPT);
     }
     ctl->next_slice = 0;
+    for (int s = 0; s < NSTAGE; ++s) ctl->stage_mq[s] = 0xffffffffu;
     mbar_fence_init();
   }
-  const int m_pad = (m + 3) & ~3;
-  for (int i = tid; i < m_pad * a.tab_stride; i += PT) tab[i] = a.table[i];  // rows >= m are +0.0
   __syncthreads();  // the only CTA-wide barrier: from here on warps meet through mbarriers only
 
   if (warp == PW) {
-    // ===================== producer warp: claims tiles, stages them with bulk TMA, publishes the
-    // threshold each tile is to be filtered at.  Tiles are claimed one at a time from a global
-    // counter, so the CTAs of the whole grid sweep the sequence as one dense window.
-    uint32_t thr_key = 0xffffffffu, bias4 = 0, pushed_key = 0;
-    float thr = THR ? a.thr : -INFINITY;
+    // ===================== producer warp: claims work items (motif, tile) from a global counter -- so
+    // the CTAs of the whole grid sweep the sequence as one dense window --, stages each tile (+ halo)
+    // with ONE bulk-TMA copy and publishes with it everything the consumers need: the threshold the
+    // tile is to be filtered at (the motif's running maximum, read from L2) and the motif's tables.
+    const uint64_t total_items = num_tiles * a.n_batch;
+    uint32_t thr_key = 0xffffffffu, bias4 = 0, pushed_key = 0, sk_last = 0;
+    float thr = -INFINITY;
+    // the motif the producer currently serves: lane l keeps word l of its filter tables
+    uint32_t cur_mq = 0xffffffffu, my_tab = 0;
+    struct {  // (scalars only: no indexed member, so it lives in registers)
+      double c0, delta, eps;
+      int m, j0, smax;
+      uint32_t pair_mul;
+      const float* table;
+      unsigned long long* block;
+      lm_hit* hits;
+      unsigned long long cap;
+      float thr;
+    } M = {0, 1, 0, 0, 0, 0, 2, nullptr, nullptr, nullptr, 0, 0.f};
     // CTA 0 measures the SM clock the scan runs at: cycle counter vs global nanosecond timer
     long long clk0 = 0;
     unsigned long long ns0 = 0;
@@ -257,42 +266,39 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       clk0 = clock64();
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
     }
-#if LM_PRUNE_PROF
-    long long p_wait = 0, p_drain = 0, p_issue = 0, p_claim = 0;
-#endif
-    uint32_t it = 0, sk_last = 0, n_end = 0, first_end = 0;
+    uint32_t it = 0, n_end = 0, first_end = 0;
     unsigned long long claim_base = 0;
     for (;; ++it) {
       const int s = it % NSTAGE;
-#if LM_PRUNE_PROF
-      const long long p00 = clock64();
-#endif
-      // claim the tile and fetch the running maximum first: both round trips overlap the wait
+      // claim the next items and fetch the running maximum first: both round trips overlap the wait
       // (CLAIM consecutive tiles per trip: the tiles are small, the L2 round trip is not)
-      unsigned long long tile = claim_base + it % CLAIM;
+      unsigned long long item = claim_base + it % CLAIM;
       uint32_t sk = sk_last;
-      if (it % CLAIM == 0) {
-        if (lane == 0) tile = atomicAdd(&a.stats[2], (unsigned long long)CLAIM);
-        if (!THR) {
-          sk = (uint32_t)(__ldcg(&a.colkeys[lane]) >> 32);
-          // row-sharded scan: the maximum the OTHER GPUs have found so far (pushed over NVLink)
-          if (a.link.world > 1 && lane == 0) sk = max(sk, peer_floor_key(a.link));
-        }
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        claim_base = tile;
+      const bool fresh = it % CLAIM == 0;
+      if (fresh) {
+        if (lane == 0) item = atomicAdd(&a.stats[2], (unsigned long long)CLAIM);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        claim_base = item;
       }
-#if LM_PRUNE_L2PF > 0
-      // the tile some CTA will claim L2PF grid rounds from now: start its trip from HBM to L2 already
-      if (lane == 0) {
-        const unsigned long long pt = tile + (unsigned long long)LM_PRUNE_L2PF * gridDim.x;
-        if (pt < num_tiles) {
-          const uint64_t pr0 = a.row_first + pt * PTILE_ROWS;
-          if (pr0 + PTILE_ROWS <= a.avail_rows) l2_prefetch_bulk(a.seq + pr0 * 32, PTILE_ROWS * 32);
-        }
+      const uint32_t mq = a.n_batch > 1 ? (uint32_t)(item / num_tiles) : 0u;
+      const unsigned long long tile = a.n_batch > 1 ? item - (unsigned long long)mq * num_tiles
+                                                    : item;
+      const bool live = item < total_items;
+      if (live && mq != cur_mq) {  // (warp-uniform) next motif: its plan, tables and result block
+        const BatchMotif* src = a.batch ? &a.batch[mq] : &a.one;
+        M.c0 = src->c0; M.delta = src->delta; M.eps = src->eps;
+        M.m = src->m; M.j0 = src->j0; M.smax = src->smax; M.pair_mul = src->pair_mul;
+        M.table = src->table; M.block = src->block; M.hits = src->hits; M.cap = src->cap; M.thr = src->thr;
+        my_tab = a.batch ? a.batch[mq].tab[lane] : a.one.tab[lane];
+        cur_mq = mq;
+        thr_key = 0xffffffffu;
+        sk_last = 0;
       }
-#endif
-      if (!THR && it % CLAIM == 0) {
-        uint32_t own = lane == 0 && a.link.world > 1 ? (uint32_t)(__ldcg(&a.colkeys[0]) >> 32) : sk;
+      if (!THR && live && (fresh || sk_last == 0)) {
+        sk = (uint32_t)(__ldcg(&M.block[lane]) >> 32);
+        // row-sharded scan: the maximum the OTHER GPUs have found so far (pushed over NVLink)
+        if (a.link.world > 1 && lane == 0) sk = max(sk, peer_floor_key(a.link));
+        uint32_t own = lane == 0 && a.link.world > 1 ? (uint32_t)(__ldcg(&M.block[0]) >> 32) : sk;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           sk = max(sk, __shfl_xor_sync(0xffffffffu, sk, o));
@@ -306,13 +312,13 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         sk_last = sk;
       }
       // ---- current threshold -> byte bias (recomputed only when the threshold moved)
-      if (THR ? it == 0 : sk != thr_key) {
-        const float t = THR ? a.thr : (sk ? key_to_f32(sk) : -INFINITY);
+      if (live && (THR ? thr_key == 0xffffffffu : sk != thr_key)) {
+        const float t = THR ? M.thr : (sk ? key_to_f32(sk) : -INFINITY);
         // sum_q >= qthr is implied by fp32score >= t (see header); 1e-6 guards the division
-        double need = ((double)t - a.plan.eps - a.plan.c0) / a.plan.delta;
+        double need = ((double)t - M.eps - M.c0) / M.delta;
         int bias;
         if (!(need > 1.0)) bias = 128;                               // everything passes
-        else if (need > (double)a.plan.smax + 2.0) bias = 0;         // nothing can pass
+        else if (need > (double)M.smax + 2.0) bias = 0;              // nothing can pass
         else {
           int qthr = (int)ceil(need - 1e-6);
           qthr = qthr < 1 ? 1 : (qthr > 128 ? 128 : qthr);
@@ -320,11 +326,11 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         }
         bias4 = (uint32_t)bias * 0x01010101u;
         thr = t;
-        thr_key = sk;
+        thr_key = THR ? 0u : sk;
       }
       // everything the reload needs is computed BEFORE the wait: between "stage free" and "copy
-      // issued" only three shared-memory stores, the expect_tx and the bulk copy remain
-#if LM_PRUNE_EXP == 2  // experiment: no DRAM traffic (the tiles cycle through an L2-resident 32 MB window)
+      // issued" only a few shared-memory stores, the expect_tx and the bulk copy remain
+#if LM_PRUNE_EXP == 2
       const uint64_t r0 = a.row_first + (tile & 1023) * PTILE_ROWS;
 #else
       const uint64_t r0 = a.row_first + tile * PTILE_ROWS;
@@ -335,65 +341,57 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       uint8_t* dst = raw + (size_t)s * S.raw_bytes;
       const uint64_t left = a.row_end > r0 ? a.row_end - r0 : 0;
       const uint32_t valid = left < PTILE_ROWS ? (uint32_t)left : PTILE_ROWS;
-#if LM_PRUNE_PROF
-      const long long p0 = clock64();
-      p_claim += p0 - p00;
-#endif
-      if (it >= NSTAGE) {
-        ring_wait(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
-#if LM_PRUNE_PROF
-        p_wait += clock64() - p0;
-        const long long d0 = clock64();
-#endif
-#if LM_PRUNE_PROF
-        p_drain += clock64() - d0;
-#endif
-      }
-#if LM_PRUNE_PROF
-      const long long p1 = clock64();
-#endif
-      if (lane == 0) {
-        ctl->desc[s].tile = tile;
-        ctl->desc[s].bias4 = bias4;
-        ctl->desc[s].thr = thr;
-        ctl->desc[s].avail = nbytes / 32;
-        ctl->desc[s].valid = valid;
-        if (tile < num_tiles) {
+      if (it >= NSTAGE) mbar_wait_backoff(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
+      TileDesc& d = ctl->desc[s];
+      if (live) {
+        if (ctl->stage_mq[s] != mq) {  // (rare) another motif moves into this stage: its recheck table and filter tables
+          float* tab = reinterpret_cast<float*>(smem + S.table_off + (size_t)s * S.table_bytes);
+          const int words = ((M.m + 3) & ~3) * a.tab_stride;
+          for (int i = lane; i < words; i += 32) tab[i] = __ldg(&M.table[i]);  // rows >= m are +0.0
+          d.tabs[lane] = my_tab;
+          if (lane == 0) ctl->stage_mq[s] = mq;
+        }
+        if (lane == 0) {
+          d.tile = tile;
+          d.block = M.block;
+          d.hits = M.hits;
+          d.cap = M.cap;
+          d.bias4 = bias4;
+          d.thr = thr;
+          d.avail = nbytes / 32;
+          d.valid = valid;
+          d.mq = mq;
+          d.m_pad = (M.m + 3) & ~3;
+          d.j0 = M.j0;
+          d.pair_mul = M.pair_mul;
+        }
+        __syncwarp();
+        if (lane == 0) {
           // (generic-proxy writes into the stage -- the consumers' padding of rows past the end of the
           // sequence -- are fenced by the writers before they release the stage)
           mbar_expect_tx(&ctl->full[s], nbytes);
           if (nbytes) tma_load_1d(dst, src, nbytes, &ctl->full[s]);
-#if LM_PRUNE_PROF
-          ctl->t_issue[s] = clock64();
-#endif
-        } else {
-          mbar_arrive(&ctl->full[s]);  // end marker: consumers read desc.tile >= num_tiles and leave
         }
-      }
-      __syncwarp();
-#if LM_PRUNE_PROF
-      p_issue += clock64() - p1;
-#endif
-      // past the end: keep handing out end markers until every consumer warp has met one (the slices
-      // of a tile go to whichever warps are free, so up to PW further slices may have been taken)
-      if (tile >= num_tiles) {
+      } else {
+        // past the end: keep handing out end markers until every consumer warp has met one (the slices
+        // of a tile go to whichever warps are free, so up to PW further slices may have been taken)
+        if (lane == 0) {
+          d.tile = ~0ull;
+          mbar_arrive(&ctl->full[s]);
+        }
         if (n_end == 0) first_end = it;
         if (++n_end > (uint32_t)((PW + SPT - 1) / SPT)) break;
       }
+      __syncwarp();
     }
-#if LM_PRUNE_PROF
-    if (blockIdx.x == 0 && lane == 0)
-      printf("cta %d producer: tiles %u  claim+wait+drain %lld (wait_empty %lld drain %lld)  empty->issued %lld cyc/tile %lld\n",
-             blockIdx.x, it, p_claim, p_wait, p_drain, p_issue, it ? p_issue / it : 0);
-#endif
     // wait until the consumers are done with the tiles still in the other stages: after that this
     // CTA's winners, hits and statistics are final
     for (uint32_t it2 = it + 1; it2 < first_end + NSTAGE; ++it2) {
       if (it2 < NSTAGE) continue;
       const int s2 = it2 % NSTAGE;
-      ring_wait(&ctl->empty[s2], ((it2 / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
+      mbar_wait_backoff(&ctl->empty[s2], ((it2 / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
     }
-    if (blockIdx.x == 0 && lane == 0 && a.stats) {
+    if (blockIdx.x == 0 && lane == 0) {
       unsigned long long ns1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
       a.stats[3] = (unsigned long long)(clock64() - clk0);
@@ -410,25 +408,24 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       done = __shfl_sync(0xffffffffu, done, 0);
       if (done == (unsigned long long)gridDim.x - 1) {
         __threadfence();
-        peer_publish(a.link, THR ? a.count - 33 : a.colkeys, lane);
+        peer_publish(a.link, a.one.block, lane);
       }
     }
     return;
   }
 
-  // ===================== consumer warps: warp w filters rows [w * WARP_ROWS, (w + 1) * WARP_ROWS) of
-  // every tile and rechecks its own candidates
+  // ===================== consumer warps: filter slices of the staged tiles, recheck their candidates
   const int q = lane & 7, g = lane >> 3;
   uint32_t* const queue = reinterpret_cast<uint32_t*>(smem + S.queue_off) + warp * QCAP;
   const uint32_t lanemask_lt = (1u << lane) - 1u;
-
-  // filter tables in per-thread registers.  They are bounced through shared
-  // memory on purpose: PRMT cannot take its table operand from a uniform
-  // register, and ptxas would otherwise keep the (uniform) kernel-parameter
-  // values in URs and re-materialise them with a UR->R move before every look-up.
+  // filter tables in per-thread registers (PRMT cannot take its table operand from a uniform register,
+  // and values that ptxas knows to be uniform would be re-materialised with a UR->R move before every
+  // look-up: hence the volatile shared-memory reads).  Reloaded when the motif changes.
   uint32_t tlo[R], thi[R];
-  {
-    if (lane < R) { queue[lane] = a.plan.tab_lo[lane]; queue[16 + lane] = a.plan.tab_hi[lane]; }
+  uint32_t cur_mq = 0xffffffffu;
+  const uint32_t one = a.one_mul;
+  if (!BATCH) {
+    if (lane < 16) { queue[lane] = a.one.tab[lane]; queue[16 + lane] = a.one.tab[16 + lane]; }
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -437,12 +434,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     }
     __syncwarp();
   }
-  const uint32_t one = a.one;
-  unsigned long long n_over = 0, n_cand = 0;
-#if LM_PRUNE_PROF
-  long long c_wait = 0, c_busy = 0, c_lat = 0, c_nlat = 0, c_t0 = clock64();
-  int hist[6] = {0, 0, 0, 0, 0, 0};
-#endif
 
   for (;;) {
     // The SPT slices of a tile (WARP_ROWS rows each) are not tied to warps: a free consumer warp takes
@@ -454,30 +445,27 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     idx = __shfl_sync(0xffffffffu, idx, 0);
     const uint32_t it = idx / SPT;
     const int s = it % NSTAGE;
-#if LM_PRUNE_PROF
-    const long long w0 = clock64();
-#endif
-    ring_wait(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
-#if LM_PRUNE_PROF
-    const long long w1 = clock64();
-    c_wait += w1 - w0;
-    if (w1 - w0 > 300) { c_lat += w1 - ctl->t_issue[s]; c_nlat += 1; }
-    {
-      const long long dw = w1 - w0;
-      hist[dw < 100 ? 0 : dw < 300 ? 1 : dw < 1000 ? 2 : dw < 2000 ? 3 : dw < 4000 ? 4 : 5] += 1;
+    mbar_wait_backoff(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
+    const TileDesc& d = ctl->desc[s];
+    if (d.tile >= num_tiles) break;
+    if (BATCH && d.mq != cur_mq) {  // (warp-uniform, rare)
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        tlo[k] = *reinterpret_cast<const volatile uint32_t*>(&d.tabs[k]);
+        thi[k] = *reinterpret_cast<const volatile uint32_t*>(&d.tabs[16 + k]);
+      }
+      cur_mq = d.mq;
     }
-#endif
-    const uint64_t tile = ctl->desc[s].tile;
-    if (tile >= num_tiles) break;
-    const uint32_t bias4 = ctl->desc[s].bias4;
-    const float thr = ctl->desc[s].thr;
+    // (only what the filter itself needs is loaded here; the recheck re-reads the rest of the descriptor
+    // when it runs -- fewer live registers across the look-up loop, which ptxas otherwise schedules worse)
+    const uint32_t bias4 = d.bias4;
     const uint32_t wrow0 = (idx % SPT) * WARP_ROWS;                  // first row of the slice in the tile
     uint8_t* rawb = raw + (size_t)s * S.raw_bytes;
     {
       // rows past the readable extent (end of the sequence only): default symbol.  Every warp fills
       // the rows IT reads; overlapping halo rows get the same value from both neighbours.
-      const uint32_t avail = ctl->desc[s].avail;
-      const uint32_t wend = wrow0 + WARP_ROWS + ((m + 3) & ~3);
+      const uint32_t avail = d.avail;
+      const uint32_t wend = wrow0 + WARP_ROWS + halo;
       if (avail < wend) {
         uint32_t w0 = (avail > wrow0 ? avail : wrow0) * 8, w1 = wend * 8;
         uint32_t fill = a.pad_fill * 0x01010101u;
@@ -486,17 +474,17 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         __syncwarp();
       }
     }
-    const uint32_t tile_valid = ctl->desc[s].valid;  // > 0 for every claimed tile
+    const uint32_t tile_valid = d.valid;  // > 0 for every claimed tile
     const uint32_t rows_valid = tile_valid > wrow0 ? min(tile_valid - wrow0, (uint32_t)WARP_ROWS) : 0;
 
-#if LM_PRUNE_EXP == 1  // experiment: stream the tiles, no filtering
+#if LM_PRUNE_EXP == 1
     if (rows_valid && bias4 == 0x12345678u) {
 #else
     if (rows_valid) {
 #endif
       // ---- filter
       const uint32_t row_base = wrow0 + g * PL;
-      const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb) + (row_base + a.plan.j0) * 8 + q;
+      const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb) + (row_base + (BATCH ? d.j0 : a.one.j0)) * 8 + q;
       // selector window.  Single mode: look-up k of position i uses row i + k.  Paired mode:
       // look-up k uses the COMBINED selector of rows (i + 2k, i + 2k + 1): symbol of the first
       // row | one class bit of the second row << 2 (8-entry table = 4 symbols x 2 classes).
@@ -505,7 +493,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       constexpr int NSEL = PAIR ? PL + W - 2 : PL + W - 1;
       uint32_t sel[NSEL];
       uint32_t raw_prev = 0;
-      const uint32_t pair_mul = a.plan.pair_mul;
+      const uint32_t pair_mul = BATCH ? d.pair_mul : a.one.pair_mul;
       auto combine = [&](uint32_t lo_row, uint32_t hi_row) {  // IMAD (FMA pipe) + LOP3
         return lo_row | ((hi_row * pair_mul) & 0x4444u);
       };
@@ -538,154 +526,141 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           nq += __popc(votes);
         }
       };
-      // Rows are processed in blocks of G (default: the thread's whole run of PL rows): the look-up
-      // loop runs k-outer / row-inner, so that consecutive PRMTs share their two table registers
-      // (operand reuse: PRMT is limited by register-file ports, not only by the ALU pipe -- measured
-      // +13 % from G = 2 to G = PL) and independent accumulator chains hide the IMAD latency.  One
-      // test covers the whole block (OR of the accumulators & mask); the rare hit re-tests pair by
-      // pair.
-      constexpr int G = LM_PRUNE_G;
+      // The look-up loop runs table-outer / row-inner over the thread's whole run of PL rows, so that
+      // consecutive PRMTs share their two table registers (operand reuse: PRMT is limited by
+      // register-file ports, not only by the ALU pipe) and independent accumulator chains hide the
+      // IMAD latency.
 #pragma unroll
-      for (int i0 = 0; i0 < PL; i0 += G) {
-        const int g = (PL - i0) < G ? (PL - i0) : G;  // compile-time after unrolling
-#pragma unroll
-        for (int ii = 0; ii < G; ++ii) {
-          if (ii < g) {
-            const int i = i0 + ii;
-            if (PAIR) {
-              const uint32_t nx = make_sel(rp[(i + W - 1) * 8]);
-              sel[i + W - 2] = combine(raw_prev, nx);
-              raw_prev = nx;
-            } else {
-              sel[i + W - 1] = make_sel(rp[(i + W - 1) * 8]);
-            }
-          }
+      for (int i = 0; i < PL; ++i) {
+        if (PAIR) {
+          const uint32_t nx = make_sel(rp[(i + W - 1) * 8]);
+          sel[i + W - 2] = combine(raw_prev, nx);
+          raw_prev = nx;
+        } else {
+          sel[i + W - 1] = make_sel(rp[(i + W - 1) * 8]);
         }
-        uint32_t acc[G];
+      }
+      uint32_t acc[PL];
 #pragma unroll
-        for (int ii = 0; ii < G; ++ii) acc[ii] = bias4;
+      for (int i = 0; i < PL; ++i) acc[i] = bias4;
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
+      for (int k = 0; k < R; ++k) {
 #pragma unroll
-          for (int ii = 0; ii < G; ++ii) {
-            if (ii < g) {
-#if LM_PRUNE_EXP == 3  // experiment: one table register per look-up (valid only when tab_hi == 0)
-              acc[ii] = add_fma_pipe(prmt_raw(tlo[k], 0u, sel[i0 + ii + STEP * k]), one, acc[ii]);
+        for (int i = 0; i < PL; ++i) acc[i] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc[i]);
+      }
+      // one test for the whole run; the rare hit narrows it down through sub-blocks of 8 rows (their
+      // ORs are by-products of the reduction) before it looks at row pairs
+      constexpr int NSUB = (PL + 7) / 8;
+      uint32_t sub[NSUB];
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u) sub[u] = 0;
+#pragma unroll
+      for (int i = 0; i < PL; ++i) sub[i >> 3] |= acc[i];
+      uint32_t any = 0;
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u) any |= sub[u];
+#if LM_PRUNE_EXP == 4
+      if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0) && bias4 == 0x12345678u) {
 #else
-              acc[ii] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i0 + ii + STEP * k]), one, acc[ii]);
-#endif
-            }
-          }
-        }
-        // one test for the whole block; the rare hit narrows it down through 4 sub-blocks of 8 rows
-        // (their ORs are by-products of the reduction) before it looks at row pairs
-        constexpr int NSUB = (G + 7) / 8;
-        uint32_t sub[NSUB];
-#pragma unroll
-        for (int u = 0; u < NSUB; ++u) sub[u] = 0;
-#pragma unroll
-        for (int ii = 0; ii < G; ++ii)
-          if (ii < g) sub[ii >> 3] |= acc[ii];
-        uint32_t any = 0;
-#pragma unroll
-        for (int u = 0; u < NSUB; ++u) any |= sub[u];
-#if LM_PRUNE_EXP == 4  // experiment: never leave the fast path (wrong results; shows what the candidates cost)
-        if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0) && bias4 == 0x12345678u) {
-#else
-        if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0)) {
+      if (__any_sync(0xffffffffu, (any & 0x80808080u) != 0)) {
 #endif
 #pragma unroll
-          for (int u = 0; u < NSUB; ++u) {
-            if (!__any_sync(0xffffffffu, (sub[u] & 0x80808080u) != 0)) continue;
+        for (int u = 0; u < NSUB; ++u) {
+          if (!__any_sync(0xffffffffu, (sub[u] & 0x80808080u) != 0)) continue;
 #pragma unroll
-            for (int ii = 8 * u; ii < 8 * u + 8 && ii < G; ii += 2) {
-              if (ii + 1 < g) push2(acc[ii], acc[ii + 1], i0 + ii);
-              else if (ii < g) push2(acc[ii], 0u, i0 + ii);
-            }
+          for (int i = 8 * u; i < 8 * u + 8 && i < PL; i += 2) {
+            if (i + 1 < PL) push2(acc[i], acc[i + 1], i);
+            else push2(acc[i], 0u, i);
           }
         }
       }
       __syncwarp();  // queue complete
 
-      const uint64_t tile_row0 = a.row_first + tile * PTILE_ROWS;  // (only the rare paths below use it)
-      // ---- exact recheck of the candidates (sequential f32 sum in the reference's order, from the
-      // tile still in shared memory)
-      if (nq && nq <= QCAP) {
-        for (uint32_t k = lane; k < nq * 8; k += 32) {
-          const uint32_t code = queue[k >> 3], b = k & 7;
-          if (!((code >> b) & 1u)) continue;
-          const uint32_t row = (code >> 11) + (b >> 2), col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
-          if (row >= tile_valid) continue;
-          float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
-                                 : exact_score(rawb, tab, m_pad, row, col);
-          if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
+      if (nq) {
+        // ---- exact recheck (sequential f32 sum in the reference's order, from the tile still in
+        // shared memory) of the queued candidates -- or, when the queue overflowed (low-complexity
+        // sequence, very low threshold), of every position of the slice.  One loop for both cases:
+        // this is cold code and the consumer loop must stay small.
+        const volatile TileDesc& dv = ctl->desc[s];
+        const float thr = dv.thr;
+        const int m_pad = dv.m_pad;
+        const float* tab = reinterpret_cast<const float*>(smem + S.table_off + (size_t)s * S.table_bytes);
+        const uint64_t tile_row0 = a.row_first + dv.tile * PTILE_ROWS;
+        const bool overflow = nq > QCAP;
+        const uint32_t n_items = overflow ? rows_valid * 32 : nq * 8;
+        for (uint32_t k = lane; k < n_items; k += 32) {
+          uint32_t row, col;
+          if (overflow) {
+            row = wrow0 + (k >> 5);
+            col = k & 31;
+          } else {
+            const uint32_t code = queue[k >> 3], b = k & 7;
+            if (!((code >> b) & 1u)) continue;
+            row = (code >> 11) + (b >> 2);
+            col = ((code >> 8) & 7u) * 4 + LANE_COL[b & 3];
+            if (row >= tile_valid) continue;
+          }
+          const float sc = a.seq_exact ? exact_score_global(a.seq_exact, a.avail_rows, a.pad_sym, tab, a.tab_stride, m_pad,
+                                                            tile_row0 + row, col)
+                                       : exact_score(rawb, tab, m_pad, row, col);
+          if (sc >= thr) record<THR>(a, d, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
         }
-        n_cand += nq;
-      }
-      // ---- a queue overflow (low-complexity sequence, very low threshold) makes the warp rescan the
-      // whole slice exactly
-      if (nq > QCAP) {
-        for (uint32_t p = lane; p < rows_valid * 32; p += 32) {
-          uint32_t row = wrow0 + (p >> 5), col = p & 31;
-          float sc = a.seq_exact ? exact_score_global(a, tab, m_pad, tile_row0 + row, col)
-                                 : exact_score(rawb, tab, m_pad, row, col);
-          if (sc >= thr) record<THR>(a, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
-        }
-        n_over += 1;
+        if (lane == 0) atomicAdd(d.block + (overflow ? 35 : 34), overflow ? 1ull : (unsigned long long)nq);
       }
     }
     __syncwarp();
-#if LM_PRUNE_PROF
-    c_busy += clock64() - w1;
-#endif
     if (lane == 0) mbar_arrive(&ctl->empty[s]);  // one more slice of the stage is done
   }
-  if (lane == 0 && a.stats) {
-    if (n_over) atomicAdd(&a.stats[1], n_over);
-    if (n_cand) atomicAdd(&a.stats[0], n_cand);
-  }
-#if LM_PRUNE_PROF
-  if (blockIdx.x == 0 && lane == 0)
-    printf("cta %d warp %d: total %lld wait_full %lld busy %lld  waits>300cyc %lld mean issue->wake %lld cyc  wait histogram "
-           "<100 %d <300 %d <1000 %d <2000 %d <4000 %d >=4000 %d\n", blockIdx.x,
-           warp, clock64() - c_t0, c_wait, c_busy, c_nlat, c_nlat ? c_lat / c_nlat : 0, hist[0], hist[1], hist[2], hist[3],
-           hist[4], hist[5]);
-#endif
 }
 
 template <bool THR>
-cudaError_t launch_r(const PruneArgs& a, int sm_count, cudaStream_t stream) {
-  if (a.row_end <= a.row_first) return cudaSuccess;
+cudaError_t launch_r(const PruneArgs& a_in, int sm_count, cudaStream_t stream) {
+  if (a_in.row_end <= a_in.row_first) return cudaSuccess;
+  PruneArgs a = a_in;
+  if (!a.batch) {  // single motif: its parameters travel in the kernel arguments
+    a.n_batch = 1;
+    a.m_max = a.plan.m;
+    BatchMotif& M = a.one;
+    for (int k = 0; k < 16; ++k) { M.tab[k] = a.plan.tab_lo[k]; M.tab[16 + k] = a.plan.tab_hi[k]; }
+    M.c0 = a.plan.c0; M.delta = a.plan.delta; M.eps = a.plan.eps;
+    M.m = a.plan.m; M.j0 = a.plan.j0; M.smax = a.plan.smax; M.pair_mul = a.plan.pair_mul;
+    M.table = a.table;
+    M.block = a.colkeys;
+    M.hits = a.hits; M.cap = a.cap; M.thr = a.thr;
+  }
   const uint64_t num_tiles = (a.row_end - a.row_first + PTILE_ROWS - 1) / PTILE_ROWS;
-  const PSmem S = psmem(a.plan.m, a.tab_stride);
+  const PSmem S = psmem(a.m_max, a.tab_stride);
   void (*kern)(const PruneArgs, uint64_t) = nullptr;
+  const bool batch = a.batch != nullptr;
+#define LM_PICK(RR, PP) kern = batch ? prune_kernel<RR, PP, THR, true> : prune_kernel<RR, PP, THR, false>; break;
   if (a.plan.pair) {
     switch (a.plan.r) {
-      case 3: kern = prune_kernel<3, true, THR>; break;
-      case 4: kern = prune_kernel<4, true, THR>; break;
-      case 5: kern = prune_kernel<5, true, THR>; break;
-      case 6: kern = prune_kernel<6, true, THR>; break;
-      case 8: kern = prune_kernel<8, true, THR>; break;
+      case 3: LM_PICK(3, true)
+      case 4: LM_PICK(4, true)
+      case 5: LM_PICK(5, true)
+      case 6: LM_PICK(6, true)
+      case 8: LM_PICK(8, true)
       default: return cudaErrorInvalidValue;
     }
   } else {
     switch (a.plan.r) {
-      case 4: kern = prune_kernel<4, false, THR>; break;
-      case 6: kern = prune_kernel<6, false, THR>; break;
-      case 8: kern = prune_kernel<8, false, THR>; break;
-      case 10: kern = prune_kernel<10, false, THR>; break;
-      case 12: kern = prune_kernel<12, false, THR>; break;
-      case 16: kern = prune_kernel<16, false, THR>; break;
+      case 4: LM_PICK(4, false)
+      case 6: LM_PICK(6, false)
+      case 8: LM_PICK(8, false)
+      case 10: LM_PICK(10, false)
+      case 12: LM_PICK(12, false)
+      case 16: LM_PICK(16, false)
       default: return cudaErrorInvalidValue;
     }
   }
+#undef LM_PICK
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PT, S.total);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  uint64_t grid = std::min<uint64_t>((uint64_t)sm_count * per_sm, num_tiles);
+  uint64_t grid = std::min<uint64_t>((uint64_t)sm_count * per_sm, num_tiles * a.n_batch);
   kern<<<(unsigned)grid, PT, S.total, stream>>>(a, num_tiles);
   return cudaGetLastError();
 }

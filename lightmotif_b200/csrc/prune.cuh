@@ -59,6 +59,24 @@ ProteinPlan plan_prune_protein(const float* pssm, size_t m, size_t stride, doubl
                                double n_positions, int force_r = 0);
 double estimate_max_score_protein(const float* pssm, size_t m, size_t stride, double n_positions);
 
+// One motif of a launch: what the kernel needs besides the sequence.  A launch may sweep MANY motifs
+// (the lightmotif-cli job loop: one resident sequence, a motif file) as long as their filters share
+// the template instance (look-ups per position, single / paired): work items are (motif, tile).
+struct BatchMotif {
+  uint32_t tab[32];            // filter tables: tab_lo[16] | tab_hi[16] of the plan
+  double c0 = 0, delta = 1, eps = 0;
+  int m = 0, j0 = 0, smax = 0;
+  uint32_t pair_mul = 2;
+  const float* table = nullptr;          // device: recheck table [m rounded up to 4][tab_stride] f32
+  // device: the motif's 512-byte result block -- u64 keys[32] (per-column winners, zero-initialised),
+  // first cell @256 B, hit count @264, statistics @272 (candidates, overflowing slices)
+  unsigned long long* block = nullptr;
+  lm_hit* hits = nullptr;                // threshold mode
+  unsigned long long cap = 0;
+  float thr = 0.f;
+  uint32_t pad_ = 0;
+};
+
 struct PruneArgs {
   const uint8_t* seq = nullptr;  // [avail_rows][32]: what the FILTER reads (DNA symbols / protein class codes)
   // protein: the residues themselves, same shape, for the exact recheck (nullptr: recheck from the tile)
@@ -70,9 +88,15 @@ struct PruneArgs {
   uint64_t row_end = 0;
   uint8_t pad_sym = 4;           // default symbol of the alphabet (exact recheck past the readable extent)
   uint8_t pad_fill = 4;          // what the FILTER sees past the readable extent (DNA: N; protein: class of X)
-  uint32_t one = 1;              // opaque multiplier: `acc = p * one + acc` keeps the byte-lane adds on the FMA pipe (IMAD)
+  uint32_t one_mul = 1;          // opaque multiplier: `acc = p * one_mul + acc` keeps the byte-lane adds on the FMA pipe (IMAD)
   const float* table = nullptr;  // device: [m rounded up to 4][tab_stride] f32, pad rows +0.0
-  PrunePlan plan;
+  PrunePlan plan;                // single motif: the whole plan; many motifs: r / pair select the kernel instance
+  // many motifs in one launch: device array of n_batch motifs, m_max = widest motif.  When `batch` is
+  // null the launcher builds `one` from plan / table / colkeys / thr / hits / cap below.
+  const BatchMotif* batch = nullptr;
+  uint32_t n_batch = 1;
+  int m_max = 0;
+  BatchMotif one;
   // argmax mode: colkeys[32] holds the running per-column winners (read for the
   // dynamic threshold, updated with atomicMax)
   unsigned long long* colkeys = nullptr;
@@ -81,9 +105,10 @@ struct PruneArgs {
   lm_hit* hits = nullptr;
   unsigned long long cap = 0;
   unsigned long long* count = nullptr;
-  // statistics: [0] candidates rechecked, [1] tiles that overflowed to the exact fallback;
-  // [2] is the dynamic tile counter (zero-initialised), [3] / [4] SM cycles / ns of CTA 0,
-  // [5] counter of finished consumer warps (zero-initialised; the last one publishes to the peers)
+  // launch-level scratch (zero-initialised): [2] the work-item counter, [3] / [4] SM cycles / ns of
+  // CTA 0, [5] counter of finished producer warps (the last one publishes to the peers).  Single-motif
+  // launches pass the statistics words of the motif's own block (block + 34), whose [0] / [1] are
+  // the motif's candidate / overflow counts.
   unsigned long long* stats = nullptr;
   // hit coordinates (threshold mode): row = row relative to row_begin + row_add,
   // position = col * pos_rows + row  (pos_rows == 0: row_end - row_begin)

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
           }
         }
         if (my_row0 == a.row_begin && lane == 0 && a.row_begin < a.row_end)
-          a.first_cell[q] = U8 ? min(accu[0], 255u) : __float_as_uint(accf[0]);
+          a.first_cell[(size_t)q * a.first_cell_stride] = U8 ? min(accu[0], 255u) : __float_as_uint(accf[0]);
         if (a.n_motifs > 1) {
           // u8: +1 so that a valid candidate never encodes to key 0 ("none")
           const uint32_t sk = U8 ? bu + 1u : f32_to_key(bf);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
             unsigned long long m = red[lane];
 #pragma unroll
             for (int w = 1; w < WARPS; ++w) { unsigned long long o = red[w * 32 + lane]; m = o > m ? o : m; }
-            if (m) atomicMax(&a.colkeys[(size_t)q * 32 + lane], m);
+            if (m) atomicMax(&a.colkeys[(size_t)q * a.colkeys_stride + lane], m);
           }
         } else {
           best_f = bf; best_u = bu; best_row = brow; best_any = any;

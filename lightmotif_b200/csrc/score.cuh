@@ -34,10 +34,11 @@ struct ScoreArgs {
   // MODE_STORE
   void* out = nullptr;
   uint64_t out_stride = 0;  // elements
-  // MODE_ARGMAX: [n_motifs][32] packed keys (score key << 32 | row), zero-initialised;
-  // first_cell[n_motifs]: raw 32-bit score of cell (row_begin, 0)
+  // MODE_ARGMAX: motif q's 32 packed keys (score key << 32 | row, zero-initialised) start at
+  // colkeys[q * colkeys_stride]; first_cell[q * first_cell_stride] = raw 32-bit score of cell (row_begin, 0)
   unsigned long long* colkeys = nullptr;
   uint32_t* first_cell = nullptr;
+  uint64_t colkeys_stride = 32, first_cell_stride = 1;
   // MODE_THRESHOLD
   uint32_t thr_bits = 0;  // f32 bits or u8 value
   lm_hit* hits = nullptr;

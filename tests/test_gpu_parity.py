@@ -376,6 +376,43 @@ def test_batch_through_filter(dna, jaspar):
     dna.set_prune(1)
 
 
+def test_batch_both_strands_cache_and_empty(lm, dna, jaspar):
+    """Strand selection of the batch calls (reverse complement = rows reversed, A<->T, C<->G,
+    pwm/mod.rs:566-577), the per-motif-set plan cache (same set twice, then a different set, then the
+    first again) and the per-entry status (a motif longer than the sequence is None)."""
+    n = 3_000_000
+    motifs = [m for m in jaspar["motifs"] if 8 <= len(m) <= 24][:24] + [jaspar["rest"]]
+    pssms = [O.pssm_from_counts(O.DNA, c, 0.1) for c in motifs]
+    # the reverse complement against its definition
+    p0 = pssms[0]
+    rc = lm.reverse_complement(p0)
+    assert np.array_equal(rc, p0[::-1][:, [2, 3, 0, 1, 4]])
+    maxw = max(len(p) for p in pssms)
+    seq = dna.sequence_synthetic(n, maxw - 1)
+    dna.set_prune(0)
+    want = []
+    for p in pssms:
+        want += [seq.score_argmax(p), seq.score_argmax(lm.reverse_complement(p))]
+    dna.set_prune(2)
+    for rep in range(2):
+        got = seq.score_argmax_batch(pssms, strands=lm.STRAND_BOTH)
+        assert got == want
+    assert seq.score_argmax_batch(pssms[:5], strands=lm.STRAND_REVERSE) == want[1:10:2]
+    assert seq.score_argmax_batch(pssms, strands=lm.STRAND_DIRECT) == want[0::2]
+    thr = [float(np.float32(w["score"] - 3.0)) for w in want[0::2]]
+    dna.set_prune(0)
+    want_hits = []
+    for p, t in zip(pssms, thr):
+        want_hits += [seq.score_threshold(p, t), seq.score_threshold(lm.reverse_complement(p), t)]
+    dna.set_prune(2)
+    assert seq.score_threshold_batch(pssms, thr, cap=4096, strands=lm.STRAND_BOTH) == want_hits
+    dna.set_prune(1)
+    # a motif longer than the sequence: None for that entry only
+    tiny = dna.sequence_from_symbols(O.synth_dna(12), maxw - 1)
+    res = tiny.score_argmax_batch([pssms[0][:4], pssms[-1]])
+    assert res[0] is not None and res[1] is None
+
+
 def test_sharded_merge_equals_single_call(lm, dna, jaspar):
     """Row slabs scored independently + lm_argmax_merge == one call (the
     multi-GPU reduction, exercised on one device)."""
