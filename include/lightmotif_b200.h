@@ -187,6 +187,12 @@ int lm_argmax_f32(lm_ctx *ctx, const float *scores, size_t rows, size_t stride,
                   int rule, lm_hit *best);
 int lm_max_f32(lm_ctx *ctx, const float *scores, size_t rows, size_t stride,
                float *best);
+/* Maximum::max as a given reference back-end computes it: LM_RULE_GENERIC / LM_RULE_SSE2 (which has
+ * no SIMD max and uses the generic one, dispatch.rs:169-177) = the true maximum; LM_RULE_AVX2 =
+ * max(0.0, maximum), because the AVX2 accumulators start at 0.0 (avx2.rs:438-441) -- what
+ * Pipeline::dispatch() returns on an x86-64 host with AVX2 for an all-negative score matrix. */
+int lm_max_f32_rule(lm_ctx *ctx, const float *scores, size_t rows, size_t stride,
+                    int rule, float *best);
 int lm_argmax_u8(lm_ctx *ctx, const uint8_t *scores, size_t rows, size_t stride,
                  int rule, lm_hit *best);
 int lm_max_u8(lm_ctx *ctx, const uint8_t *scores, size_t rows, size_t stride,

@@ -468,12 +468,15 @@ class Pipeline:
                             C.byref(best)))
         return None if st == capi.EMPTY else MatrixCoordinates(int(best.row), int(best.col))
 
-    def max(self, scores):
+    def max(self, scores, rule=RULE_GENERIC):
+        """Maximum::max; rule=RULE_AVX2 reproduces that back-end's floor at 0.0 (lm_max_f32_rule)."""
         is_u8 = scores.dtype == np.uint8
         out = C.c_uint8(0) if is_u8 else C.c_float(0)
-        fn = capi.lib().lm_max_u8 if is_u8 else capi.lib().lm_max_f32
-        st = self._check(fn(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0] // scores.itemsize,
-                            C.byref(out)))
+        if is_u8:
+            st = self._check(capi.lib().lm_max_u8(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0], C.byref(out)))
+        else:
+            st = self._check(capi.lib().lm_max_f32_rule(self._ctx, _ptr(scores), scores.shape[0], scores.strides[0] // 4,
+                                                        rule, C.byref(out)))
         return None if st == capi.EMPTY else (int(out.value) if is_u8 else np.float32(out.value))
 
     def threshold(self, scores, t, cap=None):

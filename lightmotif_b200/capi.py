@@ -51,7 +51,7 @@ SYMBOLS = [
     "lm_abi_version", "lm_strerror", "lm_ctx_last_error", "lm_ctx_create", "lm_ctx_create_on_stream",
     "lm_ctx_destroy", "lm_ctx_stream", "lm_ctx_synchronize", "lm_ctx_kernel_launches",
     "lm_ctx_last_kernel_ms", "lm_ctx_last_sm_clock_mhz", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
-    "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_argmax_u8", "lm_max_u8",
+    "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_max_f32_rule", "lm_argmax_u8", "lm_max_u8",
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
     "lm_seq_from_striped", "lm_seq_from_striped_slab", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
     "lm_seq_info", "lm_seq_device_ptr", "lm_seq_download", "lm_seq_free", "lm_seq_score_f32",
@@ -114,6 +114,7 @@ def _declare(L):
     L.lm_argmax_f32.argtypes = [vp, vp, sz, sz, i, hitp]
     L.lm_argmax_u8.argtypes = [vp, vp, sz, sz, i, hitp]
     L.lm_max_f32.argtypes = [vp, vp, sz, sz, f32p]
+    L.lm_max_f32_rule.argtypes = [vp, vp, sz, sz, i, f32p]
     L.lm_max_u8.argtypes = [vp, vp, sz, sz, u8p]
     L.lm_threshold_f32.argtypes = [vp, vp, sz, sz, C.c_float, hitp, sz, szp]
     L.lm_threshold_u8.argtypes = [vp, vp, sz, sz, C.c_uint8, hitp, sz, szp]

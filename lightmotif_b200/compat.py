@@ -64,6 +64,11 @@ class EncodedSequence:
     def __array__(self, dtype=None, copy=None):
         return np.asarray(self._data, dtype=dtype)
 
+    def __buffer__(self, flags):  # lib.rs:220-249: read-only 1-D buffer of symbol codes
+        v = self._data.view()
+        v.flags.writeable = False
+        return memoryview(v)
+
     def copy(self):
         c = object.__new__(EncodedSequence)
         c.protein, c._data = self.protein, self._data.copy()
@@ -88,9 +93,18 @@ class StripedSequence:
     def __len__(self):
         return int(self._symbols.size)
 
+    def _view(self):
+        # lib.rs:304-317, 334-364: the matrix (wrap rows included) as a read-only Fortran-ordered buffer
+        # of shape [32 columns][rows] -- mem[c, r] is the symbol at sequence index c * rows + r
+        v = self._dev.download().T
+        v.flags.writeable = False
+        return v
+
     def __array__(self, dtype=None, copy=None):
-        """The striped matrix without the wrap rows, shape [rows][32] (the buffer lib.rs exposes)."""
-        return np.asarray(self._dev.download()[: self._dev.rows], dtype=dtype)
+        return np.asarray(self._view(), dtype=dtype)
+
+    def __buffer__(self, flags):
+        return memoryview(self._view())
 
     def copy(self):
         return StripedSequence._from_symbols(self._symbols, self.protein)
@@ -153,11 +167,21 @@ class ScoringMatrix:
     def __init__(self, values, background=None, *, protein=False):
         if background is not None:
             raise NotImplementedError("custom backgrounds are outside the hot-path scope")
+        # lib.rs:729-745: the matrix starts as DenseMatrix::new (zero-filled), so a symbol missing from
+        # the dict (typically N) weighs 0.0; columns are taken in alphabet order and must agree in length
         sym = pwm._SYMBOLS[_alphabet(protein)]
-        m = len(next(iter(values.values())))
-        data = np.full((m, len(sym)), -np.inf, dtype=np.float32)
-        for ch, col in values.items():
-            data[:, sym.index(ch)] = np.asarray(list(col), dtype=np.float32)
+        data = None
+        for j, ch in enumerate(sym):
+            if ch not in values:
+                continue
+            col = np.asarray(list(values[ch]), dtype=np.float32)
+            if data is None:
+                data = np.zeros((len(col), len(sym)), dtype=np.float32)
+            if data.shape[0] != len(col):
+                raise ValueError("Invalid number of rows")
+            data[:, j] = col
+        if data is None:
+            raise ValueError("Invalid count matrix")
         self.protein, self._data = bool(protein), data
 
     @classmethod
@@ -174,6 +198,11 @@ class ScoringMatrix:
 
     def __array__(self, dtype=None, copy=None):
         return np.asarray(self._data, dtype=dtype)
+
+    def __buffer__(self, flags):  # lib.rs:676-697, 789-819: [M rows][K] f32, read-only
+        v = self._data.view()
+        v.flags.writeable = False
+        return memoryview(v)
 
     def calculate(self, sequence):
         """lib.rs:855-874: configure the wrap rows for this matrix, then score every position."""
@@ -214,8 +243,17 @@ class StripedScores:
         rows = self._m.shape[0]
         return iter(float(self._m[i % rows, i // rows]) for i in range(len(self)))
 
+    def _view(self):
+        # lib.rs:1128-1155: Fortran-ordered buffer of shape [32 columns][rows]
+        v = self._m.T
+        v.flags.writeable = False
+        return v
+
     def __array__(self, dtype=None, copy=None):
-        return np.asarray(self._m, dtype=dtype)
+        return np.asarray(self._view(), dtype=dtype)
+
+    def __buffer__(self, flags):
+        return memoryview(self._view())
 
     def threshold(self, threshold):
         rows = self._m.shape[0]
@@ -282,6 +320,10 @@ def create(sequences, *, protein=False, name=None):
         if any(ch not in sym for ch in s):
             raise ValueError("Invalid symbol in sequence")
     return Motif(CountMatrix(pwm.counts_from_sequences(_alphabet(protein), sequences), protein=protein), name)
+
+
+LIMITED_API = False  # lightmotif.lib.LIMITED_API: the buffer protocol is available (PEP 688 __buffer__)
+AVX2_SUPPORTED = False  # lightmotif.lib: the CPU back-ends are not what runs here
 
 
 def load(file, format="jaspar", *, protein=False):

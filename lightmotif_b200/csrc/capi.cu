@@ -695,6 +695,14 @@ int lm_max_f32(lm_ctx* ctx, const float* scores, size_t rows, size_t stride, flo
   if (s == LM_OK && best) *best = h.score;
   return s;
 }
+int lm_max_f32_rule(lm_ctx* ctx, const float* scores, size_t rows, size_t stride, int rule, float* best) {
+  float m = 0.f;
+  int s = lm_max_f32(ctx, scores, rows, stride, &m);
+  // avx2.rs:438-441: the AVX2 accumulators start at 0.0, so that back-end never returns less
+  if (s == LM_OK && rule == LM_RULE_AVX2 && !(m > 0.0f)) m = 0.0f;
+  if (s == LM_OK && best) *best = m;
+  return s;
+}
 int lm_max_u8(lm_ctx* ctx, const uint8_t* scores, size_t rows, size_t stride, uint8_t* best) {
   lm_hit h;
   int s = argmax_host(ctx, scores, true, rows, stride, LM_RULE_GENERIC, &h);

@@ -145,7 +145,58 @@ __global__ void __launch_bounds__(ST_THREADS, LM_ST_MINB) stripe_kernel(const ui
 
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t r0 = t * ST_ROWS;  // local row of the tile
+    // Interior tiles (every word of all 32 column segments lies inside the sequence: all but the last
+    // few of each column) take a path without any per-word bounds logic -- the general path below
+    // spends ~18 instructions per symbol on 64-bit index checks and was issue-bound at 44 % of the
+    // HBM rate.
+    const uint64_t p_last = (uint64_t)31 * rows + row0 + r0;  // first symbol of the last column's segment
+    const bool interior = ((p_last >> 2) + ST_COLW) * 4 <= n && (!FROM_ASCII || dna);
+    if (interior) {
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) {
+        const int c = warp + ci * (ST_THREADS / 32);
+        const uint32_t* seg = src32 + (((uint64_t)c * rows + row0 + r0) >> 2);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int wi = j * 32 + lane;
+          raw[ci][j] = wi < ST_COLW ? __ldg(seg + wi) : 0u;
+        }
+      }
+#pragma unroll
+      for (int ci = 0; ci < NC; ++ci) {
+        const int c = warp + ci * (ST_THREADS / 32);
+        const uint64_t p_first = (uint64_t)c * rows + row0 + r0;
+        if (lane == 0) shift[c] = (uint32_t)(p_first & 3);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int wi = j * 32 + lane;
+          if (wi >= ST_COLW) break;
+          uint32_t out = raw[ci][j];
+          if (FROM_ASCII) {
+            uint32_t code;
+            if (dna_word_fast(out, code)) {
+              out = code;
+            } else {  // N, lower case, anything else: byte by byte through the table
+              const uint32_t w = out;
+              const uint64_t p0 = ((p_first >> 2) + wi) * 4;
+              out = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                uint32_t cde = lut[(w >> (8 * b)) & 0xFF];
+                if (cde == 0xFF) {
+                  if (p0 + b < bad) bad = p0 + b;
+                  cde = pad;
+                }
+                out |= cde << (8 * b);
+              }
+            }
+          }
+          tile[c][wi] = out;
+        }
+      }
+    } else {
     fetch(t);
+
     // ---- phase 1: encode the 32 column segments (ST_ROWS consecutive symbols each) into shared memory
 #pragma unroll
     for (int ci = 0; ci < NC; ++ci) {
@@ -191,24 +242,38 @@ __global__ void __launch_bounds__(ST_THREADS, LM_ST_MINB) stripe_kernel(const ui
         tile[c][wi] = out;
       }
     }
+    }  // general path
     __syncthreads();
-    // ---- phase 2: re-align, 4x4 byte transposes, 32-byte rows written as 8 x 4 bytes
-    for (int blk = threadIdx.x; blk < (ST_ROWS / 4) * 8; blk += ST_THREADS) {
-      const int cb = blk & 7, rb = blk >> 3;
-      uint32_t w[4];
+    // ---- phase 2: re-align, 4x4 byte transposes; a thread assembles 16 bytes of 4 consecutive rows
+    // (half a striped row each) and writes them with 16-byte stores
+    for (int blk = threadIdx.x; blk < (ST_ROWS / 4) * 2; blk += ST_THREADS) {
+      const int half = blk & 1, rb = blk >> 1;
+      uint32_t o[4][4];  // [row k][column block]
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = 4 * cb + i;
-        w[i] = __funnelshift_r(tile[c][rb], tile[c][rb + 1], 8 * shift[c]);
+      for (int cbl = 0; cbl < 4; ++cbl) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 16 * half + 4 * cbl + i;
+          w[i] = __funnelshift_r(tile[c][rb], tile[c][rb + 1], 8 * shift[c]);
+        }
+        const uint32_t u = __byte_perm(w[0], w[1], 0x5140), v = __byte_perm(w[2], w[3], 0x5140);
+        const uint32_t x = __byte_perm(w[0], w[1], 0x7362), y = __byte_perm(w[2], w[3], 0x7362);
+        o[0][cbl] = __byte_perm(u, v, 0x5410);
+        o[1][cbl] = __byte_perm(u, v, 0x7632);
+        o[2][cbl] = __byte_perm(x, y, 0x5410);
+        o[3][cbl] = __byte_perm(x, y, 0x7632);
       }
-      uint32_t u = __byte_perm(w[0], w[1], 0x5140), v = __byte_perm(w[2], w[3], 0x5140);
-      uint32_t x = __byte_perm(w[0], w[1], 0x7362), y = __byte_perm(w[2], w[3], 0x7362);
-      uint32_t o[4] = {__byte_perm(u, v, 0x5410), __byte_perm(u, v, 0x7632),
-                       __byte_perm(x, y, 0x5410), __byte_perm(x, y, 0x7632)};
+      const uint64_t rbase = r0 + 4 * rb;
+      if (rbase + 3 < out_rows) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint64_t r = r0 + 4 * rb + k;
-        if (r < out_rows) *reinterpret_cast<uint32_t*>(dst + r * 32 + 4 * cb) = o[k];
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(dst + (rbase + k) * 32 + 16 * half) = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (rbase + k < out_rows)
+            *reinterpret_cast<uint4*>(dst + (rbase + k) * 32 + 16 * half) = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
       }
     }
     __syncthreads();

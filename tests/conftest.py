@@ -13,6 +13,11 @@ GOLDEN = REPO / "tests" / "golden"
 sys.path.insert(0, str(REPO))
 
 
+# the reference's own test files (scratch copy, see test_gpu_reference_pytests.py) and the
+# `lightmotif` alias package are loaded by that test only, never collected directly
+collect_ignore = ["_ref_pytests", "reference_alias"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

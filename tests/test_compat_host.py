@@ -24,3 +24,17 @@ def test_matrices_match_oracle(kat):
             call()
     with pytest.raises(ValueError):
         lightmotif.create(["ATG."])
+
+
+def test_scoring_matrix_from_dict_zero_fills_missing_symbols():
+    """lib.rs:729-745: the matrix starts zero-filled, so a symbol missing from the dict (typically N)
+    weighs 0.0, not -inf; columns of unequal length are rejected."""
+    import lightmotif_b200.compat as lightmotif
+    sm = lightmotif.ScoringMatrix({"A": [1.0, -2.0], "C": [0.5, 0.25], "T": [-1.0, 3.0], "G": [0.0, -0.5]})
+    a = np.asarray(sm)
+    assert a.shape == (2, 5) and a[:, 4].tolist() == [0.0, 0.0] and a[1].tolist() == [-2.0, 0.25, 3.0, -0.5, 0.0]
+    with pytest.raises(ValueError):
+        lightmotif.ScoringMatrix({"A": [1.0, 2.0], "C": [1.0]})
+    with pytest.raises(ValueError):
+        lightmotif.ScoringMatrix({})
+    assert memoryview(sm).shape == (2, 5)

@@ -56,8 +56,9 @@ def test_sequences(lightmotif):  # test_sequence.py
         s1[10]
     assert str(s1) == "ATGC" and np.asarray(s1).tolist() == [A, T, G, C]
     st = lightmotif.stripe("ATGC")
-    mem = np.asarray(st)
-    assert mem.shape == (1, 32) and mem[0, :4].tolist() == [A, T, G, C] and mem[0, 4] == N
+    mem = memoryview(st)  # lib.rs: Fortran-ordered [32 columns][rows]; mem[c, r] = symbol c * rows + r
+    assert mem.shape == (32, 1) and [mem[c, 0] for c in range(4)] == [A, T, G, C] and mem[4, 0] == N
+    assert memoryview(s1).shape == (4,) and memoryview(s1)[1] == T
     with pytest.raises(ValueError):
         lightmotif.EncodedSequence("ATG.")
     with pytest.raises(ValueError):
