@@ -276,6 +276,19 @@ PrunePlan cached_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, b
   return plan;
 }
 
+// Which instance of the filter kernel a single-motif scan runs: the one whose recheck enumerates
+// candidates across the warp pays off from ~5 queue entries per slice.  Predicted from the plan's pass
+// rate under a uniform background -- or, when the previous scan ran with the same plan, from the
+// density it actually met (a real genome at a modest maximum is far denser than the model says).
+bool want_dense(lm_ctx* ctx, const PrunePlan& plan) {
+  if (ctx->density >= 0.0 && ctx->density_key == ctx->plan_key) return ctx->density > 4.0;
+  return plan.est_pass_rate * prune_slice_positions() > 4.0;
+}
+void note_density(lm_ctx* ctx, uint64_t candidates, uint64_t rows) {
+  ctx->density_key = ctx->plan_key;
+  ctx->density = rows ? (double)candidates * prune_slice_positions() / ((double)rows * 32.0) : -1.0;
+}
+
 // protein: plan with a one-entry cache, recheck table [m_pad][32], class-coded copy of the sequence
 ProteinPlan cached_protein_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, bool argmax_mode, double t,
                                 double npos) {
@@ -1062,6 +1075,7 @@ int argmax_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, s
     pa.plan = plan;
     pa.colkeys = (unsigned long long*)small;
     pa.stats = (unsigned long long*)(small + 272);
+    pa.dense = !protein && want_dense(ctx, plan);
     if (linked) pa.link = *link;  // the scan kernel itself shares the maximum and publishes the block
     LM_TRY(launch_prune(false, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
     ctx->launches += 1;
@@ -1105,6 +1119,7 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) { ctx->last_ms = ms; ctx->timed = false; }
   const SmallBlock* sb = (const SmallBlock*)sl.h;
+  if (sl.pruned) note_density(ctx, sb->stats[0], sl.n_rows);
   ctx->stats[0] = sl.pruned ? sb->stats[0] : 0;
   ctx->stats[1] = sl.pruned ? sb->stats[1] : 0;
   ctx->stats[2] = sl.pruned ? 1 : 0;
@@ -1194,6 +1209,7 @@ int threshold_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m
     pa.stats = (unsigned long long*)(small + 272);
     pa.row_add = row_add;
     pa.pos_rows = pos_rows;
+    pa.dense = !protein && want_dense(ctx, plan);
     if (linked) pa.link = *link;
     LM_TRY(launch_prune(true, pa, std::max(1, ctx->sm_count - ctx->opt_reserve_sms), ctx->stream));
   } else {
@@ -1243,7 +1259,10 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
   PrunePlan plan;
   LM_CHECK(threshold_launch(ctx, seq, pssm, m, pssm_stride, row_begin, row_end, t, (lm_hit*)ctx->d_hits.p, cap,
                             SYNC_SMALL_OFF, nullptr, &plan));
-  if (plan.ok) LM_CHECK(fetch_stats(ctx, plan, SYNC_SMALL_OFF));
+  if (plan.ok) {
+    LM_CHECK(fetch_stats(ctx, plan, SYNC_SMALL_OFF));
+    note_density(ctx, ctx->stats[0], row_end - row_begin);
+  }
   return fetch_hits(ctx, hits, cap, count, SYNC_SMALL_OFF);
 }
 
@@ -1266,6 +1285,7 @@ struct BatchItem {
 };
 struct BatchGroup {
   int r = 0, pair = 0, m_max = 0;
+  uint32_t pair_mul = 2;
   std::vector<uint32_t> motifs;
   size_t desc_off = 0;  // byte offset of the group's BatchMotif array in the staged buffer
 };
@@ -1393,12 +1413,15 @@ int batch_prepare(lm_ctx* ctx, const lm_seq* seq, const float* pssms, const uint
         bytes += (size_t)table_mpad(it.m) * 8 * 4;
         int g = -1;
         for (size_t i = 0; i < B.groups.size(); ++i)
-          if (B.groups[i].r == it.plan.r && B.groups[i].pair == it.plan.pair) g = (int)i;
+          if (B.groups[i].r == it.plan.r && B.groups[i].pair == it.plan.pair &&
+              (!it.plan.pair || B.groups[i].pair_mul == it.plan.pair_mul))
+            g = (int)i;
         if (g < 0) {
           B.groups.push_back(BatchGroup());
           g = (int)B.groups.size() - 1;
           B.groups[g].r = it.plan.r;
           B.groups[g].pair = it.plan.pair;
+          B.groups[g].pair_mul = it.plan.pair_mul;
         }
         B.groups[g].motifs.push_back((uint32_t)q);
         B.groups[g].m_max = std::max(B.groups[g].m_max, (int)it.m);
@@ -1485,7 +1508,7 @@ int batch_launch(lm_ctx* ctx, const lm_seq* seq, lm_batch_cache& B, bool argmax_
   uint64_t launches = 0, n_pruned = 0;
   LM_TRY(cudaMemsetAsync(blocks, 0, n * BATCH_BLOCK + 1024, ctx->stream));
   // rows scored exactly first to seed the running maxima of the filtered argmax scans
-  const size_t boot = argmax_mode ? std::min<size_t>(n_rows, 16384) : 0;
+  const size_t boot = argmax_mode ? std::min<size_t>(n_rows, 8192) : 0;
   bool any_pruned = false;
   for (const auto& it : B.items) any_pruned = any_pruned || (it.pruned && seq->length >= it.m);
   if (argmax_mode && any_pruned && boot) {
@@ -1520,6 +1543,7 @@ int batch_launch(lm_ctx* ctx, const lm_seq* seq, lm_batch_cache& B, bool argmax_
     pa.pad_sym = pad_symbol(alphabet);
     pa.plan.r = g.r;
     pa.plan.pair = g.pair;
+    pa.plan.pair_mul = g.pair_mul;
     pa.batch = (const BatchMotif*)(dbase + g.desc_off);
     pa.n_batch = (uint32_t)g.motifs.size();
     pa.m_max = g.m_max;

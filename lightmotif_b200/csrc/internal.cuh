@@ -52,6 +52,10 @@ struct lm_ctx {
   // host-side set-up once
   std::vector<uint8_t> table_key, table8_key, plan_key;
   lm::PrunePlan plan_cache;
+  // candidates per slice observed by the last filtered single-motif scan, and the plan it ran with:
+  // the next scan with that plan picks the kernel instance accordingly (prune.cuh PruneArgs::dense)
+  std::vector<uint8_t> density_key;
+  double density = -1.0;
   // in-flight fused argmax calls (launch / finish split, LM_SLOTS slots): result blocks
   // live at d_small + slot * 1024 and are copied to pinned host memory
   struct Slot {

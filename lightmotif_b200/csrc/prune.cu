@@ -213,12 +213,83 @@ __device__ __noinline__ float exact_score_global(const uint8_t* seq_exact, uint6
   return s;
 }
 
+// Recheck of a LONG candidate queue (real genomes at a modest maximum, low thresholds: tens of
+// candidates per slice).  The in-line loop of the kernel gives each lane one FLAG of an entry --
+// usually one flag in eight is set, so seven lanes in eight idle through the exact sum.  Here the
+// set flags of 32 entries are enumerated with a warp prefix sum, so that every lane rescores a
+// distinct candidate.  Compiled only into the DENSE instances of the kernel: the consumer loop of the
+// sparse instance (one or two candidates per slice: the headline case) must stay small (instruction
+// cache), and a non-inlined call costs it registers (measured: -11 %).  The host picks the instance
+// from the candidate density the plan predicts -- or, for a matrix it has scanned before, observed.
+struct RecheckCtx {
+  const uint8_t* rawb;
+  const float* tab;
+  const uint32_t* queue;
+  unsigned long long* block;
+  lm_hit* hits;
+  unsigned long long cap;
+  uint64_t tile_row0, row_begin, row_add, pos_rows;
+  float thr;
+  int m_pad;
+  uint32_t nq, tile_valid;
+};
+template <bool THR>
+__device__ __forceinline__ void recheck_many(const RecheckCtx& c) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t base = 0; base < c.nq; base += 32) {
+    const uint32_t code = base + lane < c.nq ? c.queue[base + lane] : 0u;
+    const uint32_t cnt = __popc(code & 0xffu);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t t = 0; t < total; t += 32) {
+      const uint32_t want = t + lane;
+      uint32_t e = 0;  // entry holding candidate `want`: first lane whose inclusive count exceeds it
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl, (e + step - 1) & 31);
+        if (v <= want) e += step;
+      }
+      e &= 31;
+      const uint32_t code_e = __shfl_sync(0xffffffffu, code, e);
+      const uint32_t incl_e = __shfl_sync(0xffffffffu, incl, e);
+      if (want >= total) continue;
+      const uint32_t flags = code_e & 0xffu;
+      const uint32_t k = want - (incl_e - __popc(flags));  // k-th set flag of the entry
+      const uint32_t b = __fns(flags, 0, k + 1);
+      const uint32_t row = (code_e >> 11) + (b >> 2), col = ((code_e >> 8) & 7u) * 4 + LANE_COL[b & 3];
+      if (row >= c.tile_valid) continue;
+      const float sc = exact_score(c.rawb, c.tab, c.m_pad, row, col);
+      if (sc >= c.thr) {
+        const uint32_t rel_row = (uint32_t)(c.tile_row0 + row - c.row_begin);
+        if (THR) {
+          unsigned long long slot = atomicAdd(c.block + 33, 1ull);
+          if (slot < c.cap) {
+            lm_hit h;
+            h.row = rel_row + c.row_add;
+            h.col = col;
+            h.position = (uint64_t)col * c.pos_rows + h.row;
+            h.score = sc;
+            c.hits[slot] = h;
+          }
+        } else {
+          atomicMax(&c.block[col], ((unsigned long long)f32_to_key(sc) << 32) | rel_row);
+        }
+      }
+    }
+  }
+}
+
 // BATCH = false: one motif, whose filter parameters are kernel arguments (uniform registers) and whose
 // tables are loaded into registers once -- the instance the single-motif scans (and the headline
 // benchmark) run; BATCH = true: the parameters travel with the tiles.  The look-up loop is identical,
 // but it needs every register ptxas has (72 at 3 CTAs/SM): two more live values and it either spills
 // or gives up interleaving the selector loads with the look-ups (measured: -10 %).
-template <int R, bool PAIR, bool THR, bool BATCH>
+template <int R, bool PAIR, bool THR, bool BATCH, bool DENSE>
 __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const PruneArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -422,7 +493,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   // and values that ptxas knows to be uniform would be re-materialised with a UR->R move before every
   // look-up: hence the volatile shared-memory reads).  Reloaded when the motif changes.
   uint32_t tlo[R], thi[R];
-  uint32_t cur_mq = 0xffffffffu;
   const uint32_t one = a.one_mul;
   if (!BATCH) {
     if (lane < 16) { queue[lane] = a.one.tab[lane]; queue[16 + lane] = a.one.tab[16 + lane]; }
@@ -448,13 +518,15 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     mbar_wait_backoff(&ctl->full[s], (it / NSTAGE) & 1, LM_PRUNE_CSLEEP);
     const TileDesc& d = ctl->desc[s];
     if (d.tile >= num_tiles) break;
-    if (BATCH && d.mq != cur_mq) {  // (warp-uniform, rare)
+    if (BATCH) {
+      // the tables travel with the tile and are re-read for every slice (2 R shared-memory loads per
+      // ~750 instructions): a "did the motif change?" test would cost a live register across the
+      // look-up loop, and with it ptxas stops interleaving the selector loads with the look-ups
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         tlo[k] = *reinterpret_cast<const volatile uint32_t*>(&d.tabs[k]);
         thi[k] = *reinterpret_cast<const volatile uint32_t*>(&d.tabs[16 + k]);
       }
-      cur_mq = d.mq;
     }
     // (only what the filter itself needs is loaded here; the recheck re-reads the rest of the descriptor
     // when it runs -- fewer live registers across the look-up loop, which ptxas otherwise schedules worse)
@@ -493,7 +565,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       constexpr int NSEL = PAIR ? PL + W - 2 : PL + W - 1;
       uint32_t sel[NSEL];
       uint32_t raw_prev = 0;
-      const uint32_t pair_mul = BATCH ? d.pair_mul : a.one.pair_mul;
+      const uint32_t pair_mul = a.one.pair_mul;  // (launch-uniform: batches are grouped by it)
       auto combine = [&](uint32_t lo_row, uint32_t hi_row) {  // IMAD (FMA pipe) + LOP3
         return lo_row | ((hi_row * pair_mul) & 0x4444u);
       };
@@ -587,6 +659,16 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         const float* tab = reinterpret_cast<const float*>(smem + S.table_off + (size_t)s * S.table_bytes);
         const uint64_t tile_row0 = a.row_first + dv.tile * PTILE_ROWS;
         const bool overflow = nq > QCAP;
+        if (DENSE && !overflow && nq > 4 && !a.seq_exact) {
+          RecheckCtx c;
+          c.rawb = rawb; c.tab = tab; c.queue = queue; c.block = dv.block; c.hits = dv.hits; c.cap = dv.cap;
+          c.tile_row0 = tile_row0; c.row_begin = a.row_begin; c.row_add = a.row_add;
+          c.pos_rows = a.pos_rows ? a.pos_rows : a.row_end - a.row_begin;
+          c.thr = thr; c.m_pad = m_pad; c.nq = nq; c.tile_valid = tile_valid;
+          recheck_many<THR>(c);
+          if (lane == 0) atomicAdd(d.block + 34, (unsigned long long)nq);
+          nq = 0;
+        }
         const uint32_t n_items = overflow ? rows_valid * 32 : nq * 8;
         for (uint32_t k = lane; k < n_items; k += 32) {
           uint32_t row, col;
@@ -605,7 +687,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
                                        : exact_score(rawb, tab, m_pad, row, col);
           if (sc >= thr) record<THR>(a, d, sc, (uint32_t)(tile_row0 + row - a.row_begin), col);
         }
-        if (lane == 0) atomicAdd(d.block + (overflow ? 35 : 34), overflow ? 1ull : (unsigned long long)nq);
+        if (lane == 0 && (overflow || nq)) atomicAdd(d.block + (overflow ? 35 : 34), overflow ? 1ull : (unsigned long long)nq);
       }
     }
     __syncwarp();
@@ -617,6 +699,7 @@ template <bool THR>
 cudaError_t launch_r(const PruneArgs& a_in, int sm_count, cudaStream_t stream) {
   if (a_in.row_end <= a_in.row_first) return cudaSuccess;
   PruneArgs a = a_in;
+  a.one.pair_mul = a.plan.pair_mul;  // uniform over the launch (many-motif launches are grouped by it)
   if (!a.batch) {  // single motif: its parameters travel in the kernel arguments
     a.n_batch = 1;
     a.m_max = a.plan.m;
@@ -632,7 +715,10 @@ cudaError_t launch_r(const PruneArgs& a_in, int sm_count, cudaStream_t stream) {
   const PSmem S = psmem(a.m_max, a.tab_stride);
   void (*kern)(const PruneArgs, uint64_t) = nullptr;
   const bool batch = a.batch != nullptr;
-#define LM_PICK(RR, PP) kern = batch ? prune_kernel<RR, PP, THR, true> : prune_kernel<RR, PP, THR, false>; break;
+#define LM_PICK(RR, PP)                                                                                      \
+  kern = batch ? prune_kernel<RR, PP, THR, true, false>                                                    \
+               : (a.dense ? prune_kernel<RR, PP, THR, false, true> : prune_kernel<RR, PP, THR, false, false>); \
+  break;
   if (a.plan.pair) {
     switch (a.plan.r) {
       case 3: LM_PICK(3, true)
@@ -1140,6 +1226,8 @@ ProteinPlan plan_prune_protein(const float* pssm, size_t m, size_t stride, doubl
   best.plan.ok = best.plan.r > 0 && best_cost < exact_cost;
   return best;
 }
+
+int prune_slice_positions() { return WARP_ROWS * 32; }
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream) {
   return threshold_mode ? launch_r<true>(a, sm_count, stream) : launch_r<false>(a, sm_count, stream);

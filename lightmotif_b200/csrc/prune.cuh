@@ -91,6 +91,9 @@ struct PruneArgs {
   uint32_t one_mul = 1;          // opaque multiplier: `acc = p * one_mul + acc` keeps the byte-lane adds on the FMA pipe (IMAD)
   const float* table = nullptr;  // device: [m rounded up to 4][tab_stride] f32, pad rows +0.0
   PrunePlan plan;                // single motif: the whole plan; many motifs: r / pair select the kernel instance
+  // single-motif launches: use the kernel instance whose recheck enumerates candidates across the
+  // warp (worth it from ~5 candidates per slice of 3968 positions; costs the sparse case ~10 %)
+  bool dense = false;
   // many motifs in one launch: device array of n_batch motifs, m_max = widest motif.  When `batch` is
   // null the launcher builds `one` from plan / table / colkeys / thr / hits / cap below.
   const BatchMotif* batch = nullptr;
@@ -118,5 +121,7 @@ struct PruneArgs {
 };
 
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream);
+// positions one consumer warp filters at a time (the granularity of the recheck queue)
+int prune_slice_positions();
 
 }  // namespace lm

@@ -41,6 +41,8 @@
 // accumulator pair: half the instructions per update, the same sequential order per position --
 // still bit-identical.  The pair codes 8 s + 32 s' come from the pre-multiplied window words with
 // a funnel shift and a multiply-add per 4 symbols.
+#include <algorithm>
+
 #include "score.cuh"
 
 namespace lm {
@@ -169,7 +171,13 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
     if (nrows) tma_load_1d(raw + (size_t)buf * L.raw_bytes, a.seq + r0 * 32, nrows * 32, &bars[buf]);
   };
 
-  uint64_t tile = blockIdx.x;
+  // many motifs over few tiles (the seeding launch of a batch): the grid is num_tiles x motif_chunks
+  // CTAs, CTA (tile, chunk) applies its chunk of the motifs to its one tile
+  const uint32_t chunks = a.motif_chunks > 1 ? a.motif_chunks : 1;
+  const uint32_t chunk = chunks > 1 ? (uint32_t)(blockIdx.x / num_tiles) : 0;
+  const int q_begin = (int)((uint64_t)a.n_motifs * chunk / chunks), q_end = (int)((uint64_t)a.n_motifs * (chunk + 1) / chunks);
+  const uint64_t step = chunks > 1 ? num_tiles : gridDim.x;
+  uint64_t tile = chunks > 1 ? blockIdx.x % num_tiles : blockIdx.x;
   if (tid == 0 && tile < num_tiles) stage(tile, 0);
 
   // running per-column best of this thread's column (single-motif argmax):
@@ -179,9 +187,9 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
   bool best_any = false;
 
   uint32_t it = 0;
-  for (; tile < num_tiles; tile += gridDim.x, ++it) {
+  for (; tile < num_tiles; tile += step, ++it) {
     const int buf = it & 1;
-    const uint64_t next = tile + gridDim.x;
+    const uint64_t next = tile + step;
     if (tid == 0 && next < num_tiles) stage(next, buf ^ 1);
     mbar_wait(&bars[buf], (it >> 1) & 1);
 
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
     const uint32_t* colp = tilet + lane * L.tsw + warp * (RPT / 4);
     const uint64_t my_row0 = tile_row0 + (uint64_t)warp * RPT;  // absolute striped row of acc[0]
 
-    for (int q = 0; q < a.n_motifs; ++q) {
+    for (int q = q_begin; q < q_end; ++q) {
       // ---- motif table -> shared memory
       int m_pad = a.m_pads ? a.m_pads[q] : a.m_pad;
       {
@@ -404,8 +412,15 @@ cudaError_t launch_mode(int mode, const ScoreArgs& a, int sm_count, cudaStream_t
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sm_count * per_sm;
-  if (grid > num_tiles) grid = num_tiles;
-  kern<<<(unsigned)grid, THREADS, L.total, stream>>>(a, num_tiles);
+  ScoreArgs b = a;
+  b.motif_chunks = 1;
+  if (a.n_motifs > 1 && num_tiles * 2 <= grid) {  // fewer tiles than CTAs: split the motifs as well
+    b.motif_chunks = (uint32_t)std::min<uint64_t>(grid / num_tiles, (uint64_t)a.n_motifs);
+    grid = num_tiles * b.motif_chunks;
+  } else if (grid > num_tiles) {
+    grid = num_tiles;
+  }
+  kern<<<(unsigned)grid, THREADS, L.total, stream>>>(b, num_tiles);
   return cudaGetLastError();
 }
 

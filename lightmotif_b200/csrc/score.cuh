@@ -31,6 +31,7 @@ struct ScoreArgs {
   const int* m_pads = nullptr;          // device, [n_motifs] (nullptr: use m_pad)
   int m_pad = 0;                        // single motif / max over the batch
   int n_motifs = 1;
+  uint32_t motif_chunks = 1;            // set by the launcher (see score.cu)
   // MODE_STORE
   void* out = nullptr;
   uint64_t out_stride = 0;  // elements
