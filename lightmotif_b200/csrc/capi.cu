@@ -266,11 +266,17 @@ PrunePlan cached_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, b
   std::vector<uint8_t> key = matrix_key(argmax_mode ? 4 : 5, LM_DNA, pssm, m, stride, 4);
   double extra[4] = {argmax_mode ? 0.0 : t, npos, (double)ctx->opt_filter_rows, (double)ctx->opt_filter_mode};
   key.insert(key.end(), (const uint8_t*)extra, (const uint8_t*)extra + sizeof(extra));
-  if (key == ctx->plan_key) return ctx->plan_cache;
+  const bool replan = argmax_mode && ctx->replan_state == 1 && key == ctx->replan_key;
+  if (key == ctx->plan_key && !replan) return ctx->plan_cache;
+  if (!replan && key != ctx->replan_key) ctx->replan_state = 0;  // another matrix: forget the observation
+  const double t_plan = replan ? ctx->replan_t : estimate_max_score(pssm, m, stride, npos);
   PrunePlan plan = argmax_mode
-      ? plan_prune(pssm, m, stride, estimate_max_score(pssm, m, stride, npos), true, npos, ctx->opt_filter_rows,
-                   ctx->opt_filter_mode)
+      ? plan_prune(pssm, m, stride, t_plan, true, npos, ctx->opt_filter_rows, ctx->opt_filter_mode)
       : plan_prune(pssm, m, stride, t, false, npos, ctx->opt_filter_rows, ctx->opt_filter_mode);
+  if (replan) {
+    ctx->replan_state = 2;
+    ctx->density = -1.0;  // the observed density belonged to the old plan
+  }
   ctx->plan_key.swap(key);
   ctx->plan_cache = plan;
   return plan;
@@ -1119,7 +1125,8 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) { ctx->last_ms = ms; ctx->timed = false; }
   const SmallBlock* sb = (const SmallBlock*)sl.h;
-  if (sl.pruned) note_density(ctx, sb->stats[0], sl.n_rows);
+  if (sl.pruned) note_density(ctx, sb->stats[0] + 128 * sb->stats[1], sl.n_rows);  // (an overflowing slice had > 128 entries)
+  const bool flooded = sl.pruned && ctx->density > 8.0 && ctx->replan_state == 0;
   ctx->stats[0] = sl.pruned ? sb->stats[0] : 0;
   ctx->stats[1] = sl.pruned ? sb->stats[1] : 0;
   ctx->stats[2] = sl.pruned ? 1 : 0;
@@ -1130,7 +1137,13 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
   if (per_column) std::memcpy(per_column, cw, sizeof(cw));
   const float fc = bits_to_score(sb->ck.first_cell, false);
   if (first_cell) *first_cell = fc;
-  return apply_rule(cw, fc, rule, false, sl.n_rows, 0, best);
+  const int rs = apply_rule(cw, fc, rule, false, sl.n_rows, 0, best);
+  if (flooded && rs == LM_OK && std::isfinite(best->score)) {  // plan the next scan of this matrix for the real maximum
+    ctx->replan_key = ctx->plan_key;
+    ctx->replan_t = (double)best->score;
+    ctx->replan_state = 1;
+  }
+  return rs;
 }
 
 void* lm_ctx_result_block(lm_ctx* ctx, int slot) {
@@ -1261,7 +1274,7 @@ int lm_seq_score_threshold_f32(lm_ctx* ctx, const lm_seq* seq, const float* pssm
                             SYNC_SMALL_OFF, nullptr, &plan));
   if (plan.ok) {
     LM_CHECK(fetch_stats(ctx, plan, SYNC_SMALL_OFF));
-    note_density(ctx, ctx->stats[0], row_end - row_begin);
+    note_density(ctx, ctx->stats[0] + 128 * ctx->stats[1], row_end - row_begin);
   }
   return fetch_hits(ctx, hits, cap, count, SYNC_SMALL_OFF);
 }

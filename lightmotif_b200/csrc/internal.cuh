@@ -56,6 +56,13 @@ struct lm_ctx {
   // the next scan with that plan picks the kernel instance accordingly (prune.cuh PruneArgs::dense)
   std::vector<uint8_t> density_key;
   double density = -1.0;
+  // argmax scans plan their filter for the maximum a uniform-random sequence of that length would
+  // reach; a sequence whose real maximum is far lower (a real genome without a strong site) floods
+  // that filter with candidates.  When a scan observes that, the next scan with the same matrix is
+  // planned for the maximum actually found (once per matrix).
+  std::vector<uint8_t> replan_key;   // plan key the observation belongs to
+  double replan_t = 0.0;
+  int replan_state = 0;              // 0 none, 1 pending (use replan_t at the next plan), 2 done
   // in-flight fused argmax calls (launch / finish split, LM_SLOTS slots): result blocks
   // live at d_small + slot * 1024 and are copied to pinned host memory
   struct Slot {

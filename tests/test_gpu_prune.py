@@ -292,3 +292,49 @@ def test_all_default_symbols_and_minus_infinity(dna):
         assert (got["row"], got["col"]) == (exact["row"], exact["col"]) == (rr, cc), r
     dna.set_prune(2)
     assert seq.score_threshold(pssm, 0.0) == []
+
+
+def test_dense_candidates_and_replanning_stay_exact(lm, dna, jaspar, ecoli_codes):
+    """Sequences without a strong site for the motif: the filter planned for the maximum of a
+    uniform-random sequence floods with candidates.  The scan that observes it switches the next
+    scans of the same matrix to the dense-candidate kernel instance and to a plan for the maximum
+    actually found -- every scan must still return exactly what scoring every cell returns, for
+    argmax (all rules) and for thresholds with thousands of hits."""
+    from lightmotif_b200 import pwm
+    pssm = pwm.pssm_from_counts(pwm.DNA, jaspar["rest"], 0.1)
+    rng = np.random.default_rng(5)
+    inputs = {"ecoli x4": np.tile(ecoli_codes, 4),
+              "two-letter": rng.integers(0, 2, 12_000_000).astype(np.uint8)}  # A / C only: REST never scores high
+    for name, codes in inputs.items():
+        seq = dna.sequence_from_symbols(codes, len(pssm) - 1)
+        # a deliberately weak filter (4 single-row look-ups) on the second input: certain flooding
+        dna.set_filter_rows(4 if name == "two-letter" else 0)
+        dna.set_filter_mode(1 if name == "two-letter" else 0)
+        dna.set_prune(0)
+        want = {rule: seq.score_argmax(pssm, rule=rule) for rule in (0, 1, 2)}
+        t = want[1]["score"] - 8.0
+        want_hits = seq.score_threshold(pssm, t)
+        assert len(want_hits) > 200
+        dna.set_boot_rows(4096)
+        dna.set_prune(2)
+        seen = []
+        for rep in range(4):
+            for rule in (0, 1, 2):
+                assert seq.score_argmax(pssm, rule=rule) == want[rule], (name, rep, rule)
+            st = dna.last_stats
+            seen.append((st["filter_rows"], st["paired"], st["rechecked"], st["overflow_tiles"]))
+        work = [c + 128 * o for _, _, c, o in seen]
+        assert work[-1] <= work[0], seen  # re-planning never makes the filter weaker
+        if name == "two-letter":
+            assert work[0] > 8 * codes.size / 3968, seen  # it did flood
+        for rep in range(3):  # first the sparse, then (if dense) the enumerating instance
+            assert seq.score_threshold(pssm, t) == want_hits, (name, rep)
+        # another matrix in between: observations are per matrix
+        other = pwm.pssm_from_counts(pwm.DNA, jaspar["motifs"][5], 0.1)
+        dna.set_prune(0)
+        w2 = seq.score_argmax(other)
+        dna.set_prune(2)
+        assert seq.score_argmax(other) == w2 and seq.score_argmax(pssm) == want[1]
+        seq.free()
+    dna.set_filter_rows(0)
+    dna.set_filter_mode(0)
