@@ -262,8 +262,12 @@ int upload_table8(lm_ctx* ctx, const float* pssm, size_t m, size_t stride) {
 
 // plan_prune with a one-entry cache (same matrix, same threshold situation)
 PrunePlan cached_plan(lm_ctx* ctx, const float* pssm, size_t m, size_t stride, bool argmax_mode, double t,
-                      double npos) {
+                      double npos, uint64_t seq_id) {
   std::vector<uint8_t> key = matrix_key(argmax_mode ? 4 : 5, LM_DNA, pssm, m, stride, 4);
+  if (ctx->replan_state && seq_id != ctx->replan_seq) {  // the observation was about another sequence
+    if (ctx->replan_state == 2 && key == ctx->plan_key) ctx->plan_key.clear();
+    ctx->replan_state = 0;
+  }
   double extra[4] = {argmax_mode ? 0.0 : t, npos, (double)ctx->opt_filter_rows, (double)ctx->opt_filter_mode};
   key.insert(key.end(), (const uint8_t*)extra, (const uint8_t*)extra + sizeof(extra));
   const bool replan = argmax_mode && ctx->replan_state == 1 && key == ctx->replan_key;
@@ -1051,7 +1055,7 @@ int argmax_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, s
       pplan = cached_protein_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
       plan = pplan.plan;
     } else {
-      plan = cached_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos);
+      plan = cached_plan(ctx, pssm, m, pssm_stride, true, 0.0, npos, seq->id);
     }
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }
@@ -1098,6 +1102,7 @@ int argmax_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, s
   LM_TRY(cudaEventRecord(sl.done, ctx->stream));
   sl.state = 1;
   sl.n_rows = n_rows;
+  sl.seq_id = seq->id;
   sl.pruned = plan.ok;
   sl.r = plan.r | (plan.pair << 8);
   return LM_OK;
@@ -1141,6 +1146,7 @@ int lm_seq_score_argmax_f32_finish(lm_ctx* ctx, int slot, int rule, lm_hit* best
   if (flooded && rs == LM_OK && std::isfinite(best->score)) {  // plan the next scan of this matrix for the real maximum
     ctx->replan_key = ctx->plan_key;
     ctx->replan_t = (double)best->score;
+    ctx->replan_seq = sl.seq_id;
     ctx->replan_state = 1;
   }
   return rs;
@@ -1184,7 +1190,7 @@ int threshold_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m
       pplan = cached_protein_plan(ctx, pssm, m, pssm_stride, false, (double)t, npos);
       plan = pplan.plan;
     } else {
-      plan = cached_plan(ctx, pssm, m, pssm_stride, false, (double)t, npos);
+      plan = cached_plan(ctx, pssm, m, pssm_stride, false, (double)t, npos, seq->id);
     }
     if (ctx->opt_prune == 2 && plan.r > 0) plan.ok = true;
   }

@@ -62,6 +62,7 @@ struct lm_ctx {
   // planned for the maximum actually found (once per matrix).
   std::vector<uint8_t> replan_key;   // plan key the observation belongs to
   double replan_t = 0.0;
+  uint64_t replan_seq = 0;           // lm_seq::id the observation was made on
   int replan_state = 0;              // 0 none, 1 pending (use replan_t at the next plan), 2 done
   // in-flight fused argmax calls (launch / finish split, LM_SLOTS slots): result blocks
   // live at d_small + slot * 1024 and are copied to pinned host memory
@@ -70,6 +71,7 @@ struct lm_ctx {
     void* h = nullptr;  // pinned SmallBlock
     int state = 0;      // 0 idle, 1 in flight, 2 in flight but empty (LM_EMPTY)
     size_t n_rows = 0;
+    uint64_t seq_id = 0;
     bool pruned = false;
     int r = 0;
   } slots[LM_SLOTS];
