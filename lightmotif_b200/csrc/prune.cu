@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->full[s], 32);  // every lane of the producer warp arrives: each one releases its own writes
       mbar_init(&ctl->empty[s], SPT);
     }
     ctl->next_slice = 0;
@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       if (it >= NSTAGE) mbar_wait_backoff(&ctl->empty[s], ((it / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
       TileDesc& d = ctl->desc[s];
       if (live) {
-        if (ctl->stage_mq[s] != mq) {  // (rare) another motif moves into this stage: its recheck table and filter tables
+        uint32_t in_stage = 0;
+        if (lane == 0) in_stage = ctl->stage_mq[s];
+        in_stage = __shfl_sync(0xffffffffu, in_stage, 0);
+        if (in_stage != mq) {  // (rare) another motif moves into this stage: its recheck table and filter tables
           float* tab = reinterpret_cast<float*>(smem + S.table_off + (size_t)s * S.table_bytes);
           const int words = ((M.m + 3) & ~3) * a.tab_stride;
           for (int i = lane; i < words; i += 32) tab[i] = __ldg(&M.table[i]);  // rows >= m are +0.0
@@ -442,14 +445,14 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
           // sequence -- are fenced by the writers before they release the stage)
           mbar_expect_tx(&ctl->full[s], nbytes);
           if (nbytes) tma_load_1d(dst, src, nbytes, &ctl->full[s]);
+        } else {
+          mbar_arrive(&ctl->full[s]);  // (release: this lane's table words are visible to the consumers)
         }
       } else {
         // past the end: keep handing out end markers until every consumer warp has met one (the slices
         // of a tile go to whichever warps are free, so up to PW further slices may have been taken)
-        if (lane == 0) {
-          d.tile = ~0ull;
-          mbar_arrive(&ctl->full[s]);
-        }
+        if (lane == 0) d.tile = ~0ull;
+        mbar_arrive(&ctl->full[s]);
         if (n_end == 0) first_end = it;
         if (++n_end > (uint32_t)((PW + SPT - 1) / SPT)) break;
       }
@@ -654,10 +657,16 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         // sequence, very low threshold), of every position of the slice.  One loop for both cases:
         // this is cold code and the consumer loop must stay small.
         const volatile TileDesc& dv = ctl->desc[s];
-        const float thr = dv.thr;
-        const int m_pad = dv.m_pad;
+        // (lane 0 reads the descriptor and is the lane that releases the stage below)
+        float thr = 0.f;
+        int m_pad = 0;
+        unsigned long long dtile = 0;
+        if (lane == 0) { thr = dv.thr; m_pad = dv.m_pad; dtile = dv.tile; }
+        thr = __shfl_sync(0xffffffffu, thr, 0);
+        m_pad = __shfl_sync(0xffffffffu, m_pad, 0);
+        dtile = __shfl_sync(0xffffffffu, dtile, 0);
         const float* tab = reinterpret_cast<const float*>(smem + S.table_off + (size_t)s * S.table_bytes);
-        const uint64_t tile_row0 = a.row_first + dv.tile * PTILE_ROWS;
+        const uint64_t tile_row0 = a.row_first + dtile * PTILE_ROWS;
         const bool overflow = nq > QCAP;
         if (DENSE && !overflow && nq > 4 && !a.seq_exact) {
           RecheckCtx c;

@@ -63,4 +63,35 @@ eh = pseq.score_threshold(pp, e["score"] - 6.0)
 prot.set_prune(2)
 assert pseq.score_argmax(pp) == e and prot.last_stats["pruned"]
 assert pseq.score_threshold(pp, e["score"] - 6.0) == eh
+# dense-candidate instance: scan twice at a low threshold (the second scan has seen the density)
+dna.set_prune(2); dna.set_filter_mode(0)
+dna.set_prune(0)
+low = seq.score_threshold(pssm, 2.0)
+dna.set_prune(2)
+for _ in range(3):
+    assert seq.score_threshold(pssm, 2.0) == low
+# both strands through the batch call
+dna.set_prune(0)
+both_want = []
+for p in pssms:
+    both_want += [seq.score_argmax(p), seq.score_argmax(lm.reverse_complement(p))]
+dna.set_prune(2)
+assert seq.score_argmax_batch(pssms, strands=lm.STRAND_BOTH) == both_want
+# row-sharded scans through a communicator (three ranks on this device): shared maximum, result
+# blocks published by the scan kernels, hit lists gathered through the exchange buffers
+comm = lm.Comm.local([0, 0, 0])
+for p in comm.pipelines:
+    p.set_boot_rows(512)
+    p.set_prune(2)
+slabs = comm.shard_from_striped(st, n, 19)
+r, c = O.argmax(want, O.RULE_AVX2)
+for k in range(3):
+    g = comm.score_argmax(slabs, pssm)
+    assert (g["row"], g["col"]) == (r, c), g
+sh = comm.score_threshold(slabs, pssm, 8.0)
+ro, co = O.threshold(want, 8.0)
+assert [(h["row"], h["col"]) for h in sh] == list(zip(ro.tolist(), co.tolist()))
+for sl in slabs:
+    sl.free()
+comm.close()
 print("sanitize smoke ok", best, e)
