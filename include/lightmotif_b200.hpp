@@ -675,6 +675,64 @@ class Scanner {
   size_t block_size_ = 256;
 };
 
+// ---------------------------------------------------------- ShardedSequence
+// A configured StripedSequence cut into row slabs on N GPUs of the box (one process drives them:
+// lm_comm_init).  The sharding axis is the row range of Score::score_rows_into (pli/mod.rs:72-77);
+// score_argmax / score_threshold return what ONE call over the whole matrix returns (same tie rule,
+// positions of the whole matrix).  The same device may be listed more than once (tests).
+template <typename A>
+class ShardedSequence {
+ public:
+  ShardedSequence(const StripedSequence<A>& striped, const std::vector<int>& devices) : length_(striped.len()) {
+    lm_comm* raw = nullptr;
+    int st = lm_comm_init((int)devices.size(), devices.data(), 0, &raw);
+    if (st == LM_ERR_UNSUPPORTED) throw UnsupportedBackend();
+    if (st < 0) throw BackendError(st, "lm_comm_init");
+    comm_ = std::shared_ptr<lm_comm>(raw, lm_comm_destroy);
+    slabs_.assign(devices.size(), nullptr);
+    st = lm_comm_shard_from_striped(raw, A::ID, striped.matrix().data(), striped.rows(), striped.wrap(),
+                                    striped.matrix().stride(), striped.len(), slabs_.data());
+    if (st < 0) throw BackendError(st, std::string("lm_comm_shard_from_striped: ") + lm_comm_last_error(raw));
+  }
+  ~ShardedSequence() {
+    for (size_t i = 0; i < slabs_.size(); ++i)
+      if (slabs_[i]) lm_seq_free(lm_comm_ctx(comm_.get(), (int)i), slabs_[i]);
+  }
+  ShardedSequence(const ShardedSequence&) = delete;
+  ShardedSequence& operator=(const ShardedSequence&) = delete;
+
+  std::optional<Hit> score_argmax(const ScoringMatrix<A>& pssm, int rule = LM_RULE_AVX2) const {
+    lm_hit h;
+    int st = lm_seq_score_argmax_f32_sharded(comm_.get(), slabs_.data(), pssm.matrix().data(), pssm.len(),
+                                             pssm.matrix().stride(), rule, &h);
+    if (st == LM_EMPTY) return std::nullopt;
+    if (st < 0) throw BackendError(st, std::string("lm_seq_score_argmax_f32_sharded: ") + lm_comm_last_error(comm_.get()));
+    return Hit{(size_t)h.position, h.score};
+  }
+  // every position p with p + M <= len whose exact f32 score is >= t (Scanner semantics), sorted
+  std::vector<Hit> scan(const ScoringMatrix<A>& pssm, float t) const {
+    std::vector<lm_hit> buf(4096);
+    size_t n = 0;
+    for (;;) {
+      int st = lm_seq_score_threshold_f32_sharded(comm_.get(), slabs_.data(), pssm.matrix().data(), pssm.len(),
+                                                  pssm.matrix().stride(), t, buf.data(), buf.size(), &n, nullptr);
+      if (st == LM_ERR_OVERFLOW && n > buf.size()) { buf.resize(n); continue; }
+      if (st < 0) throw BackendError(st, std::string("lm_seq_score_threshold_f32_sharded: ") + lm_comm_last_error(comm_.get()));
+      break;
+    }
+    std::vector<Hit> out;
+    for (size_t i = 0; i < n; ++i)
+      if (buf[i].position + pssm.len() <= length_) out.push_back(Hit{(size_t)buf[i].position, buf[i].score});
+    std::sort(out.begin(), out.end(), [](const Hit& a, const Hit& b) { return a.position < b.position; });
+    return out;
+  }
+
+ private:
+  std::shared_ptr<lm_comm> comm_;
+  std::vector<lm_seq*> slabs_;
+  size_t length_;
+};
+
 template <typename A>
 void StripedSequence<A>::configure(const Pipeline<A>& pli, const ScoringMatrix<A>& pssm) {
   if (pssm.len() > 0) configure_wrap(pli, pssm.len() - 1);
