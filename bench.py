@@ -583,25 +583,45 @@ def run_ours(args):
             s.free()
             return r
 
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
-        sync_all()
-        n_e2e = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            r_e2e = e2e_step()
-        sync_all()
-        dt = time.perf_counter() - t0
+        def e2e_run(mode, threads):
+            pli.set_upload(mode, threads)
+            for _ in range(min(args.warmup, 2)):
+                e2e_step()
+            sync_all()
+            n = max(3, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(n):
+                r = e2e_step()
+            sync_all()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return total / (dt / n) / 1e9, n, r, pli.last_upload
+
+        # the ranks of one host share its cores: every rank packs with its share (one core feeds the copy engine)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        up_threads = max(1, cores // world - 1)
+        plain_gbps, _, r_plain, _ = e2e_run(0, 0)
+        e2e_gbps, n_e2e, r_e2e, up = e2e_run(1, up_threads)
+        pcie = torch.tensor([up["pcie_bytes"]], dtype=torch.float64, device=dev)
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": total / (dt / n_e2e) / 1e9, "unit": "Gbp/s",
-               "h2d_bytes_per_step": int(harr.nbytes) * world + int(pssm.nbytes) * world,
+            dist.all_reduce(pcie)
+        e2e = {"value": e2e_gbps, "unit": "Gbp/s",
+               "h2d_bytes_per_step": int(pcie.item()) + int(pssm.nbytes) * world,
                "d2h_bytes_per_step": 272 if world == 1 else (320 + 320 * world + 8) * world,
                "steps": n_e2e,
+               "host_matrix_bytes_per_step": int(harr.nbytes) * world,
+               "upload": {"how": "lm_seq_from_striped, LM_OPT_UPLOAD=1: the copy engine pulls plain 8 MiB chunks from the front of the "
+                                 "pinned matrix while host threads pack chunks from its back 4 symbols per byte; a kernel expands them "
+                                 "in place (device matrix byte-identical, tests/test_gpu_parity.py::test_packed_upload_*)",
+                          "host_threads_per_rank": up["threads"], "packed_chunks_rank0": up["packed_chunks"],
+                          "plain_chunks_rank0": up["plain_chunks"]},
+               "plain_copy": {"value": plain_gbps, "unit": "Gbp/s", "note": "LM_OPT_UPLOAD=0: the whole matrix as one 1 B/symbol copy (round 1's path)"},
                "api": ("lm_seq_from_striped(pinned host StripedSequence) + lm_seq_score_argmax_f32" if world == 1 else
                        "lm_seq_from_striped_slab(pinned host slab) + lm_comm_score_argmax_f32_launch / _finish")}
+        assert r_plain["position"] == res["position"], (r_plain, res)
         assert r_e2e["position"] == res["position"], (r_e2e, res)
         del host, harr
     else:

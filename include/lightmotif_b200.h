@@ -135,7 +135,22 @@ float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
  * sequence and reuse it while sequence and class map are unchanged, 0 = rebuild
  * it on every call */
 #define LM_OPT_CLASS_CACHE 6
+/* lm_seq_from_striped[_slab] of a large DNA matrix (pinned or pageable host
+ * memory): 1 (default) = the copy engine pulls plain chunks from the front of
+ * the matrix while host threads pack chunks from its back 4 symbols per byte
+ * (chunks holding N go as they are) and a kernel expands them in place -- the
+ * device matrix is byte-identical, the call is no longer bound by 1 B/symbol
+ * over PCIe; 0 = plain copy; 2 = packed chunks only. */
+#define LM_OPT_UPLOAD 7
+/* host threads that pack (0 = default: all hardware threads but one) */
+#define LM_OPT_UPLOAD_THREADS 8
+/* matrices smaller than this many bytes take the plain copy (default 64 MiB) */
+#define LM_OPT_UPLOAD_MIN_BYTES 9
 int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
+/* the most recent lm_seq_from_striped[_slab]: out[0] = bytes that crossed PCIe,
+ * out[1] = chunks sent packed, out[2] = chunks sent plain, out[3] = host
+ * threads used (0: plain copy) */
+int lm_ctx_last_upload(const lm_ctx *ctx, uint64_t out[4]);
 /* statistics of the most recent fused call: out[0] = cells rechecked exactly,
  * out[1] = tiles that fell back to exact scoring, out[2] = 1 if the filter
  * path ran, out[3] = filter look-ups per position | (paired mode << 8) */

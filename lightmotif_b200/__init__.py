@@ -401,6 +401,21 @@ class Pipeline:
         """LM_OPT_BOOT_ROWS: rows scored exactly before the filtered argmax scan."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 2, int(rows)))
 
+    def set_upload(self, mode=1, threads=0, min_bytes=None):
+        """LM_OPT_UPLOAD (0 plain copy, 1 plain + packed chunks, 2 packed chunks only), LM_OPT_UPLOAD_THREADS
+        (0 = all hardware threads but one), LM_OPT_UPLOAD_MIN_BYTES: how sequence_from_striped moves a large
+        DNA matrix to the device."""
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 7, int(mode)))
+        self._check(capi.lib().lm_ctx_set_option(self._ctx, 8, int(threads)))
+        if min_bytes is not None:
+            self._check(capi.lib().lm_ctx_set_option(self._ctx, 9, int(min_bytes)))
+
+    @property
+    def last_upload(self):
+        out = (C.c_uint64 * 4)()
+        self._check(capi.lib().lm_ctx_last_upload(self._ctx, C.byref(out)))
+        return {"pcie_bytes": int(out[0]), "packed_chunks": int(out[1]), "plain_chunks": int(out[2]), "threads": int(out[3])}
+
     @property
     def last_stats(self):
         out = (C.c_uint64 * 4)()

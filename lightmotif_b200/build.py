@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liblightmotif_b200.so"
-SOURCES = ["capi.cu", "comm.cu", "score.cu", "prune.cu", "seqops.cu", "reduce.cu"]
+SOURCES = ["capi.cu", "comm.cu", "score.cu", "prune.cu", "seqops.cu", "reduce.cu", "upload.cu", "hostpack.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # no --use_fast_math: f32 scores must stay IEEE (no ftz, no re-association)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
@@ -32,7 +32,7 @@ def stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "lightmotif_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "lightmotif_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

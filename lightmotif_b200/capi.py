@@ -50,7 +50,7 @@ _lib = None
 SYMBOLS = [
     "lm_abi_version", "lm_strerror", "lm_ctx_last_error", "lm_ctx_create", "lm_ctx_create_on_stream",
     "lm_ctx_destroy", "lm_ctx_stream", "lm_ctx_synchronize", "lm_ctx_kernel_launches",
-    "lm_ctx_last_kernel_ms", "lm_ctx_last_sm_clock_mhz", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
+    "lm_ctx_last_kernel_ms", "lm_ctx_last_sm_clock_mhz", "lm_ctx_set_option", "lm_ctx_last_stats", "lm_ctx_last_upload", "lm_encode", "lm_encode_lossy", "lm_stripe", "lm_configure_wrap",
     "lm_score_f32_rows", "lm_score_u8_rows", "lm_argmax_f32", "lm_max_f32", "lm_max_f32_rule", "lm_argmax_u8", "lm_max_u8",
     "lm_threshold_f32", "lm_threshold_u8", "lm_seq_from_ascii", "lm_seq_from_symbols",
     "lm_seq_from_striped", "lm_seq_from_striped_slab", "lm_seq_from_device", "lm_seq_synthetic", "lm_seq_configure_wrap",
@@ -105,6 +105,7 @@ def _declare(L):
     L.lm_ctx_last_sm_clock_mhz.restype = C.c_float
     L.lm_ctx_set_option.argtypes = [vp, i, i]
     L.lm_ctx_last_stats.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
+    L.lm_ctx_last_upload.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     L.lm_encode.argtypes = [vp, i, vp, sz, vp, szp]
     L.lm_encode_lossy.argtypes = [vp, i, vp, sz, vp]
     L.lm_stripe.argtypes = [vp, i, vp, sz, vp, sz]

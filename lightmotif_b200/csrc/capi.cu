@@ -472,6 +472,7 @@ void lm_ctx_destroy(lm_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_table, &ctx->d_table2, &ctx->d_small, &ctx->d_hits, &ctx->d_class})
     if (b->p) cudaFree(b->p);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  free_uploader(ctx->uploader);
   free_batch_cache(ctx->batch);
   for (auto& sl : ctx->slots) {
     if (sl.ev0) cudaEventDestroy(sl.ev0);
@@ -517,11 +518,29 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
     ctx->opt_class_cache = value;
     return LM_OK;
   }
+  if (option == LM_OPT_UPLOAD && value >= 0 && value <= 2) {
+    ctx->opt_upload = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_UPLOAD_THREADS && value >= 0) {
+    ctx->opt_upload_threads = value;
+    return LM_OK;
+  }
+  if (option == LM_OPT_UPLOAD_MIN_BYTES && value >= 0) {
+    ctx->opt_upload_min_bytes = value;
+    return LM_OK;
+  }
   if (option == LM_OPT_BOOT_ROWS && value >= 1) {
     ctx->opt_boot_rows = (size_t)value;
     return LM_OK;
   }
   return LM_ERR_INVALID_ARG;
+}
+
+int lm_ctx_last_upload(const lm_ctx* ctx, uint64_t out[4]) {
+  if (!ctx || !out) return LM_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = ctx->upload_stats[i];
+  return LM_OK;
 }
 
 int lm_ctx_last_stats(const lm_ctx* ctx, uint64_t out[4]) {
@@ -838,8 +857,15 @@ int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t r
   lm_seq* s = nullptr;
   LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, length, &s));
   cudaError_t e = cudaSuccess;
-  if (rows + wrap)
+  if (upload_wants_packed(ctx, alphabet, stride, (rows + wrap) * 32)) {
+    // large DNA matrix: plain copy from the front, 2-bit packed chunks from the back (upload.cu)
+    int st = upload_striped_dna(ctx, s->data, data, (rows + wrap) * 32);
+    if (st < 0) { lm_seq_free(ctx, s); return st; }
+  } else if (rows + wrap) {
     e = copy_rows(s->data, 32, data, stride, 32, rows + wrap, cudaMemcpyHostToDevice, ctx->stream);
+    ctx->upload_stats[0] = (rows + wrap) * 32;
+    ctx->upload_stats[1] = ctx->upload_stats[2] = ctx->upload_stats[3] = 0;
+  }
   if (e == cudaSuccess)
     e = cudaMemsetAsync(s->data + (rows + wrap) * 32, pad_symbol(alphabet), SLACK_ROWS * 32, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

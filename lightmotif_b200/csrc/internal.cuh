@@ -15,6 +15,9 @@
 struct lm_batch_cache;  // capi.cu: the last motif set of the batch calls, planned and staged
 void free_batch_cache(lm_batch_cache* b);
 
+struct lm_uploader;  // upload.cu: pinned ring, streams and events of the packed upload
+void free_uploader(lm_uploader* u);
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -79,6 +82,12 @@ struct lm_ctx {
   bool batch_staged = false;                      // d_table still holds that set's tables
   void* h_pin = nullptr;                          // pinned host staging
   size_t h_pin_bytes = 0;
+  // large striped DNA matrices from host memory (lm_seq_from_striped): two-ended upload, upload.cu
+  lm_uploader* uploader = nullptr;
+  int opt_upload = 1;                             // LM_OPT_UPLOAD: 0 plain copy, 1 plain + packed chunks, 2 packed chunks only
+  int opt_upload_threads = 0;                     // LM_OPT_UPLOAD_THREADS: host threads that pack (0 = all but one)
+  long long opt_upload_min_bytes = 64ll << 20;    // LM_OPT_UPLOAD_MIN_BYTES: smaller matrices take the plain copy
+  uint64_t upload_stats[4] = {0, 0, 0, 0};        // last upload: bytes over PCIe, packed chunks, plain chunks, threads
 };
 
 struct lm_seq {
@@ -140,6 +149,9 @@ int argmax_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, s
 int threshold_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m, size_t pssm_stride, size_t row_begin,
                      size_t row_end, float t, lm_hit* d_hits, size_t cap, size_t small_off, const lm::PeerLink* link,
                      lm::PrunePlan* plan_out);
+// upload.cu
+bool upload_wants_packed(const lm_ctx* ctx, int alphabet, size_t stride, size_t bytes);
+int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t bytes);
 int check_score_args(size_t m, size_t rows, size_t wrap, size_t length, size_t row_begin, size_t row_end);
 
 }  // namespace lmi

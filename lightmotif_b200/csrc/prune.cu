@@ -57,6 +57,9 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #ifndef LM_PRUNE_EXP
 #define LM_PRUNE_EXP 0       // experiments (timing only, wrong results): 1 = stream the tiles without filtering,
 #endif                       // 2 = tiles cycle through an L2-resident window, 4 = never leave the fast path
+#ifndef LM_PRUNE_ADD3
+#define LM_PRUNE_ADD3 0      // experiment: pairs of look-ups summed by one IADD3 instead of two IMADs
+#endif
 #ifndef LM_PRUNE_SPT
 #define LM_PRUNE_SPT 8       // slices (one warp's worth of rows) per staged tile
 #endif
@@ -618,11 +621,29 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       uint32_t acc[PL];
 #pragma unroll
       for (int i = 0; i < PL; ++i) acc[i] = bias4;
+#if LM_PRUNE_ADD3 > 0
+      // experiment: the first LM_PRUNE_ADD3 PAIRS of look-ups are summed with one 3-input add (IADD3, ALU pipe)
+      // instead of two IMADs (FMA pipe): fewer issue slots, more ALU-pipe work
+      constexpr int NP3 = (LM_PRUNE_ADD3 < R / 2 ? LM_PRUNE_ADD3 : R / 2);
+#pragma unroll
+      for (int kp = 0; kp < NP3; ++kp) {
+#pragma unroll
+        for (int i = 0; i < PL; ++i)
+          acc[i] = acc[i] + prmt_raw(tlo[2 * kp], thi[2 * kp], sel[i + STEP * 2 * kp]) +
+                   prmt_raw(tlo[2 * kp + 1], thi[2 * kp + 1], sel[i + STEP * (2 * kp + 1)]);
+      }
+#pragma unroll
+      for (int k = 2 * NP3; k < R; ++k) {
+#pragma unroll
+        for (int i = 0; i < PL; ++i) acc[i] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc[i]);
+      }
+#else
 #pragma unroll
       for (int k = 0; k < R; ++k) {
 #pragma unroll
         for (int i = 0; i < PL; ++i) acc[i] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc[i]);
       }
+#endif
       // one test for the whole run; the rare hit narrows it down through sub-blocks of 8 rows (their
       // ORs are by-products of the reduction) before it looks at row pairs
       constexpr int NSUB = (PL + 7) / 8;
@@ -724,6 +745,12 @@ cudaError_t launch_r(const PruneArgs& a_in, int sm_count, cudaStream_t stream) {
   const PSmem S = psmem(a.m_max, a.tab_stride);
   void (*kern)(const PruneArgs, uint64_t) = nullptr;
   const bool batch = a.batch != nullptr;
+#ifdef LM_PRUNE_ONLY  // experiment builds (tools/build_variants.py): the headline instance only
+  if constexpr (!THR) {
+    if (a.plan.pair && a.plan.r == 6 && !batch && !a.dense) kern = prune_kernel<6, true, false, false, false>;
+  }
+  if (!kern) return cudaErrorInvalidValue;
+#else
 #define LM_PICK(RR, PP)                                                                                      \
   kern = batch ? prune_kernel<RR, PP, THR, true, false>                                                    \
                : (a.dense ? prune_kernel<RR, PP, THR, false, true> : prune_kernel<RR, PP, THR, false, false>); \
@@ -749,6 +776,7 @@ cudaError_t launch_r(const PruneArgs& a_in, int sm_count, cudaStream_t stream) {
     }
   }
 #undef LM_PICK
+#endif
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

@@ -178,6 +178,28 @@ static void test_resident(const Pipeline<Dna>& pli) {  // fused calls on a resid
   CHECK(thrown);
 }
 
+// the same sequence cut into row slabs on a communicator (one process, the device listed twice so
+// that one GPU suffices): whole-matrix positions, same winner, same hits (pli/mod.rs:72-77 row axis)
+static void test_sharded(const Pipeline<Dna>& pli) {
+  auto pssm = build_pssm(pli);
+  std::string text;
+  for (int i = 0; i < 300; ++i) text += SEQUENCE;  // 19 200 symbols = 600 rows
+  auto striped = pli.stripe(pli.encode(text));
+  striped.configure(pli, pssm);
+  auto dev = pli.upload_ascii(text, pssm.len() - 1);
+  auto one = pli.score_argmax(pssm, dev);
+  ShardedSequence<Dna> sharded(striped, {0, 0, 0});
+  auto best = sharded.score_argmax(pssm);
+  CHECK(one.has_value() && best.has_value() && best->position == one->position && best->score == one->score);
+  Scanner<Dna> scanner(pli, pssm, dev);
+  auto want = scanner.threshold(-10.0f).collect();
+  auto got = sharded.scan(pssm, -10.0f);
+  CHECK(got.size() == want.size() && got.size() >= 900);
+  bool same = got.size() == want.size();
+  for (size_t i = 0; same && i < got.size(); ++i) same = got[i].position == want[i].position && got[i].score == want[i].score;
+  CHECK(same);
+}
+
 // --host: no GPU needed.  Exercises the host-side value types (matrix copies, alignment,
 // CountMatrix -> ScoringMatrix -> DiscreteMatrix) and prints the PSSM bit patterns so that the
 // pytest wrapper can compare them with the oracle's restatement of pwm/mod.rs.
@@ -231,6 +253,7 @@ int main(int argc, char** argv) {
     test_argmax_threshold(pli);
     test_score_position(pli);
     test_resident(pli);
+    test_sharded(pli);
   } catch (const UnsupportedBackend& e) {
     std::printf("UNSUPPORTED: %s\n", e.what());
     return 77;

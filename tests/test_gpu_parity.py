@@ -467,3 +467,66 @@ def test_launch_finish_pipeline(lm, dna, jaspar):
                {k: g[k] for k in ("row", "col", "position", "score", "first_cell")}
     with pytest.raises(lm.LightmotifError):
         seq.score_argmax_finish(slot=1)  # nothing in flight
+
+
+# ------------------------------------------------------------------ packed upload (upload.cu)
+
+def _random_striped(rng, rows, wrap, n_frac=0.0):
+    a = rng.integers(0, 4, size=(rows + wrap, 32), dtype=np.uint8)
+    if n_frac:
+        a[rng.random(a.shape) < n_frac] = 4
+    return a
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_packed_upload_is_byte_identical(lm, dna, mode, pinned):
+    """lm_seq_from_striped of a large DNA matrix (plain chunks from the front, 2-bit packed chunks from the
+    back, chunks with N as they are) leaves exactly the caller's bytes on the device."""
+    import torch
+    rng = np.random.default_rng(7 + mode)
+    rows, wrap = (41 << 20) // 32 + 77, 19          # 6 chunks of 8 MiB, the last one ragged
+    a = _random_striped(rng, rows, wrap)
+    a[(3 << 20) // 32 * 8 + 5, 7] = 4               # one N in the fourth chunk: that chunk goes plain
+    a[-1, 31] = 4                                   # and one in the very last byte
+    if pinned:
+        host = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
+        host.numpy()[:] = a
+        src = host.numpy()
+    else:
+        src = a
+    dna.set_upload(mode, threads=3, min_bytes=0)
+    try:
+        seq = dna.sequence_from_striped(src, rows * 32, wrap)
+        up = dna.last_upload
+        got = seq.download()
+        seq.free()
+    finally:
+        dna.set_upload(1, 0, 64 << 20)
+    assert np.array_equal(got[: rows + wrap], a)
+    assert up["packed_chunks"] + up["plain_chunks"] == 6 and up["threads"] == 3
+    assert up["plain_chunks"] >= 2                   # the two chunks holding N
+    if mode == 2 or not pinned:
+        assert up["plain_chunks"] == 2 and up["pcie_bytes"] < a.nbytes // 2
+
+
+def test_packed_upload_scan_equals_plain(lm, dna, jaspar):
+    """Same fused scan results whichever way the matrix travelled."""
+    rng = np.random.default_rng(11)
+    pssm = O.pssm_from_counts(O.DNA, jaspar["rest"], 0.1)
+    m = pssm.shape[0]
+    rows, wrap = (20 << 20) // 32, m - 1
+    a = _random_striped(rng, rows, wrap, n_frac=1e-7)
+    a[rows:] = np.roll(a[:wrap], -1, axis=1)          # wrap rows as configure_wrap leaves them (seq.rs:384-400)
+    a[rows:, 31] = 4
+    res = []
+    for mode in (0, 1, 2):
+        dna.set_upload(mode, threads=2, min_bytes=0)
+        try:
+            seq = dna.sequence_from_striped(a, rows * 32, wrap)
+            res.append((seq.score_argmax(pssm), seq.score_threshold(pssm, 8.0)))
+            seq.free()
+        finally:
+            dna.set_upload(1, 0, 64 << 20)
+    assert res[0] == res[1] == res[2]
+    assert res[0][0] is not None
