@@ -57,12 +57,6 @@ constexpr int PT = (PW + 1) * 32;       // + one producer warp
 #ifndef LM_PRUNE_EXP
 #define LM_PRUNE_EXP 0       // experiments (timing only, wrong results): 1 = stream the tiles without filtering,
 #endif                       // 2 = tiles cycle through an L2-resident window, 4 = never leave the fast path
-#ifndef LM_PRUNE_ADD3
-#define LM_PRUNE_ADD3 0      // experiment: pairs of look-ups summed by one IADD3 instead of two IMADs
-#endif
-#ifndef LM_PRUNE_ASYNC
-#define LM_PRUNE_ASYNC 0     // experiment (rejected, profiles/README.md): candidates rechecked by a dedicated warp
-#endif
 #ifndef LM_PRUNE_SPT
 #define LM_PRUNE_SPT 8       // slices (one warp's worth of rows) per staged tile
 #endif
@@ -83,7 +77,6 @@ constexpr int PTILE_ROWS = SPT * WARP_ROWS;
 constexpr int CLAIM = PW / SPT > 0 ? PW / SPT : 1;  // consecutive tiles a producer claims per trip to the global counter
 static_assert(NSTAGE * SPT > PW + SPT - 1 || NSTAGE * SPT >= 2 * PW, "ring too shallow for the slices in flight");
 constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
-constexpr int RING = 256;               // candidate ring of the recheck warp (entries; power of two)
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
 // What a consumer warp needs to know about the tile in a stage.  Everything that depends on the
@@ -108,10 +101,7 @@ struct Ctl {
   uint64_t full[NSTAGE], empty[NSTAGE];
   uint32_t next_slice;      // slices (WARP_ROWS rows of a tile) handed out to the consumer warps so far
   uint32_t stage_mq[NSTAGE];  // motif whose recheck table each stage's table slot holds (producer only)
-  // candidate ring of the recheck warp (ASYNC instances): tickets handed out / entries consumed so far
-  uint32_t ring_tail, ring_head, consumers_done, recheck_done;
   TileDesc desc[NSTAGE];
-  unsigned long long ring[RING];
 };
 struct PSmem {
   uint32_t table_off, table_bytes, ctl_off, queue_off, raw_off, raw_bytes, total;
@@ -158,26 +148,21 @@ __device__ __constant__ const uint8_t LANE_COL[4] = {0, 2, 1, 3};
 
 // a cell that reaches the threshold: hit record (threshold mode) or per-column winner (argmax mode)
 template <bool THR>
-__device__ __forceinline__ void record_to(const PruneArgs& a, unsigned long long* block, lm_hit* hits, unsigned long long cap,
-                                          float s, uint32_t rel_row, uint32_t col) {
+__device__ __forceinline__ void record(const PruneArgs& a, const TileDesc& d, float s, uint32_t rel_row, uint32_t col) {
   if (THR) {
-    unsigned long long slot = atomicAdd(block + 33, 1ull);
-    if (slot < cap) {
+    unsigned long long slot = atomicAdd(d.block + 33, 1ull);
+    if (slot < d.cap) {
       lm_hit h;
       h.row = rel_row + a.row_add;
       h.col = col;
       h.position = (uint64_t)col * (a.pos_rows ? a.pos_rows : a.row_end - a.row_begin) + h.row;
       h.score = s;
-      hits[slot] = h;
+      d.hits[slot] = h;
     }
   } else {
     unsigned long long key = ((unsigned long long)f32_to_key(s) << 32) | rel_row;
-    atomicMax(&block[col], key);
+    atomicMax(&d.block[col], key);
   }
-}
-template <bool THR>
-__device__ __forceinline__ void record(const PruneArgs& a, const TileDesc& d, float s, uint32_t rel_row, uint32_t col) {
-  record_to<THR>(a, d.block, d.hits, d.cap, s, rel_row, col);
 }
 
 // exact sequential f32 score of the window starting at (row_in_tile, col).  The table is padded
@@ -313,15 +298,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
   const uint32_t tt = PTILE_ROWS + halo;  // rows staged per tile (tile + halo of the widest motif)
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + S.ctl_off);
   uint8_t* raw = smem + S.raw_off;
-  // ASYNC (single motif, sparse candidates -- the headline instance): one of the filter warps' seats goes
-  // to a RECHECK warp.  A filter warp that meets candidates only hands them over (a ring in shared
-  // memory) and carries on filtering; the recheck warp rescores them exactly from the sequence in
-  // global memory (the tile was just read: L2 hits), several candidates at a time, and records the
-  // winners / hits.  Measured: the in-line recheck cost the filter warps 12 % (divergence, a
-  // 250-cycle dependent chain per candidate, and its code in their loop); 7 filter warps that never
-  // leave their loop outrun 8 that do.
-  constexpr bool ASYNC = LM_PRUNE_ASYNC && !BATCH && !DENSE;
-  constexpr int NCW = ASYNC ? PW - 1 : PW;  // filter warps; warp NCW = producer, warp NCW + 1 = recheck warp (ASYNC)
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -329,84 +305,12 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       mbar_init(&ctl->empty[s], SPT);
     }
     ctl->next_slice = 0;
-    ctl->ring_tail = ctl->ring_head = ctl->consumers_done = ctl->recheck_done = 0;
     for (int s = 0; s < NSTAGE; ++s) ctl->stage_mq[s] = 0xffffffffu;
     mbar_fence_init();
   }
-  if (ASYNC) {  // (tags of a previous launch's ring would pass for this launch's first lap)
-    for (int i = tid; i < RING; i += PT) ctl->ring[i] = 0ull;
-  }
   __syncthreads();  // the only CTA-wide barrier: from here on warps meet through mbarriers only
 
-  if (ASYNC && warp == NCW + 1) {
-    // ===================== recheck warp: entries = pairs of quad rows (8 byte-lane flags), 4 entries = 32 lanes
-    // per round; entry = tag (ticket / RING + 1, 21 bits) | absolute row (32) | column quad (3) | flags (8)
-    const float* tab = reinterpret_cast<const float*>(smem + S.table_off);  // (one motif: every stage holds its table;
-    const int m_pad = (a.one.m + 3) & ~3;                                   //  stage 0's is valid before the first candidate)
-    const uint8_t* sym = a.seq_exact ? a.seq_exact : a.seq;
-    volatile uint32_t* v_tail = &ctl->ring_tail;
-    volatile uint32_t* v_done = &ctl->consumers_done;
-    volatile unsigned long long* v_ring = ctl->ring;
-    uint32_t head = 0;
-    unsigned long long n_entries = 0;
-    for (;;) {
-      uint32_t avail = *v_tail - head;
-      if (avail == 0) {
-        if (*v_done == (uint32_t)NCW) {
-          if (*v_tail == head) break;
-          continue;
-        }
-        __nanosleep(1000);
-        continue;
-      }
-      // one entry per lane: a round costs one or two L2 round trips whatever the number of entries, so the
-      // warp keeps up by taking everything that has queued up meanwhile
-      const uint32_t n = avail < 32u ? avail : 32u;
-      unsigned long long entry = 0;
-      if ((uint32_t)lane < n) {
-        const uint32_t ticket = head + lane;
-        const unsigned long long expect = (unsigned long long)((ticket / RING + 1u) & 0x1fffffu);
-        do {
-          entry = v_ring[ticket % RING];
-        } while ((entry >> 43) != expect);
-      }
-      __threadfence_block();  // (acquire: the motif's table, written before the tile that produced the entry)
-      __syncwarp();
-      head += n;
-      n_entries += n;
-      if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&ctl->ring_head) = head;  // the slots may be reused
-      // argmax: only scores that reach the running maximum (as of the latest tile staged: a lower bound of the
-      // final maximum) can be winners -- without this test every candidate would end in an atomic on the same
-      // 32 keys, which the producers of the whole grid read with every tile they claim
-      const float thr = THR ? a.one.thr : *reinterpret_cast<const volatile float*>(&ctl->desc[0].thr);
-      uint32_t flags = (uint32_t)lane < n ? (uint32_t)(entry & 0xffull) : 0u;
-      while (flags) {
-        const uint32_t b = __ffs(flags) - 1;
-        flags &= flags - 1;
-        const uint64_t row = ((entry >> 11) & 0xffffffffull) + (b >> 2);
-        const uint32_t col = (uint32_t)((entry >> 8) & 7ull) * 4 + LANE_COL[b & 3];
-        if (row >= a.row_end) continue;
-#if LM_PRUNE_EXP == 5
-        continue;
-#endif
-        // (a compact rolled loop: this warp's code shares the instruction cache with the filter loop, which
-        // sits at its edge -- an unrolled version with all loads in flight cost the filter warps 25 % in
-        // instruction-fetch stalls.  Latency does not matter here: up to 32 entries are in flight per round.)
-        const float sc = exact_score_global(sym, a.avail_rows, a.pad_sym, tab, a.tab_stride, m_pad, row, col);
-        if (sc >= thr) record_to<THR>(a, a.one.block, a.one.hits, a.one.cap, sc, (uint32_t)(row - a.row_begin), col);
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {
-      if (n_entries) atomicAdd(a.one.block + 34, n_entries);
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(&ctl->recheck_done) = 1u;
-    }
-    return;
-  }
-  if (warp > NCW) return;  // (no such warp today: PT = (PW + 1) * 32)
-
-  if (warp == NCW) {
+  if (warp == PW) {
     // ===================== producer warp: claims work items (motif, tile) from a global counter -- so
     // the CTAs of the whole grid sweep the sequence as one dense window --, stages each tile (+ halo)
     // with ONE bulk-TMA copy and publishes with it everything the consumers need: the threshold the
@@ -550,7 +454,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         if (lane == 0) d.tile = ~0ull;
         mbar_arrive(&ctl->full[s]);
         if (n_end == 0) first_end = it;
-        if (++n_end > (uint32_t)((NCW + SPT - 1) / SPT)) break;
+        if (++n_end > (uint32_t)((PW + SPT - 1) / SPT)) break;
       }
       __syncwarp();
     }
@@ -560,10 +464,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       if (it2 < NSTAGE) continue;
       const int s2 = it2 % NSTAGE;
       mbar_wait_backoff(&ctl->empty[s2], ((it2 / NSTAGE) - 1) & 1, LM_PRUNE_PSLEEP);
-    }
-    if (ASYNC) {  // ... and the recheck warp with the candidates they left it
-      while (*reinterpret_cast<volatile uint32_t*>(&ctl->recheck_done) == 0u) __nanosleep(200);
-      __threadfence();
     }
     if (blockIdx.x == 0 && lane == 0) {
       unsigned long long ns1;
@@ -718,10 +618,15 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       uint32_t acc[PL];
 #pragma unroll
       for (int i = 0; i < PL; ++i) acc[i] = bias4;
-#if LM_PRUNE_ADD3 > 0
-      // experiment: the first LM_PRUNE_ADD3 PAIRS of look-ups are summed with one 3-input add (IADD3, ALU pipe)
-      // instead of two IMADs (FMA pipe): fewer issue slots, more ALU-pipe work
+      // The adds are IMADs (`p * 1 + acc`, FMA pipe) beside the PRMTs on the ALU pipe.  NP3 PAIRS of look-ups are
+      // instead summed by one 3-input add (IADD3, ALU pipe): two issue slots fewer per pair, one more ALU-pipe
+      // instruction.  Measured on the headline instance (paired R = 6): one pair +1.4 %, two -1 %, three -4 %
+      // (the ALU pipe becomes the limiter); other instances keep NP3 = 0 (not measured).
+#ifdef LM_PRUNE_ADD3
       constexpr int NP3 = (LM_PRUNE_ADD3 < R / 2 ? LM_PRUNE_ADD3 : R / 2);
+#else
+      constexpr int NP3 = (PAIR && R == 6 && !BATCH && !DENSE) ? 1 : 0;
+#endif
 #pragma unroll
       for (int kp = 0; kp < NP3; ++kp) {
 #pragma unroll
@@ -734,13 +639,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
 #pragma unroll
         for (int i = 0; i < PL; ++i) acc[i] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc[i]);
       }
-#else
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-#pragma unroll
-        for (int i = 0; i < PL; ++i) acc[i] = add_fma_pipe(prmt_raw(tlo[k], thi[k], sel[i + STEP * k]), one, acc[i]);
-      }
-#endif
       // one test for the whole run; the rare hit narrows it down through sub-blocks of 8 rows (their
       // ORs are by-products of the reduction) before it looks at row pairs
       constexpr int NSUB = (PL + 7) / 8;
@@ -769,31 +667,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       }
       __syncwarp();  // queue complete
 
-#if LM_PRUNE_EXP == 6
-      if (ASYNC && nq <= QCAP) nq = 0;
-#endif
-      if (ASYNC && nq && nq <= QCAP) {
-        // ---- hand the candidates to the recheck warp and carry on
-        const volatile TileDesc& dv = ctl->desc[s];
-        unsigned long long dtile = 0;
-        uint32_t base = 0;
-        if (lane == 0) {
-          dtile = dv.tile;
-          base = atomicAdd(&ctl->ring_tail, nq);
-        }
-        dtile = __shfl_sync(0xffffffffu, dtile, 0);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const uint64_t tile_row0 = a.row_first + dtile * PTILE_ROWS;
-        __threadfence_block();
-        for (uint32_t k = lane; k < nq; k += 32) {
-          const uint32_t ticket = base + k, code = queue[k];
-          while (ticket - *reinterpret_cast<volatile uint32_t*>(&ctl->ring_head) >= (uint32_t)RING) __nanosleep(200);  // ring full (rare)
-          const unsigned long long entry = ((unsigned long long)((ticket / RING + 1u) & 0x1fffffu) << 43) |
-                                           ((tile_row0 + (code >> 11)) << 11) | (code & 0x7ffu);
-          *reinterpret_cast<volatile unsigned long long*>(&ctl->ring[ticket % RING]) = entry;
-        }
-        nq = 0;
-      }
       if (nq) {
         // ---- exact recheck (sequential f32 sum in the reference's order, from the tile still in
         // shared memory) of the queued candidates -- or, when the queue overflowed (low-complexity
@@ -824,7 +697,7 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         const uint32_t n_items = overflow ? rows_valid * 32 : nq * 8;
         for (uint32_t k = lane; k < n_items; k += 32) {
           uint32_t row, col;
-          if (ASYNC || overflow) {  // (ASYNC: only an overflowing queue is handled here)
+          if (overflow) {
             row = wrow0 + (k >> 5);
             col = k & 31;
           } else {
@@ -844,11 +717,6 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl->empty[s]);  // one more slice of the stage is done
-  }
-  if (ASYNC) {  // this warp will hand over no more candidates
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) atomicAdd(&ctl->consumers_done, 1u);
   }
 }
 
