@@ -25,6 +25,18 @@ constexpr size_t SLACK_ROWS = 64;      // readable rows kept behind rows + wrap
 constexpr size_t SMALL_BYTES = 1 << 20;  // keys / counters block
 // d_small: launch slot s owns [s * 1024, s * 1024 + 512); the synchronous calls use the block below
 constexpr size_t SYNC_SMALL_OFF = (size_t)LM_SLOTS * 1024;
+
+// Some kernel instances keep a few bytes per thread on the stack.  The driver reserves a device's local
+// memory lazily, at the first launch that needs it -- and that launch synchronises with every kernel running
+// on the device.  A row-sharded scan keeps a kernel spinning until the OTHER ranks have published
+// (gather_wait_kernel): when two ranks share a device (tests, lm_comm_init with a device listed twice) the
+// late rank's first launch would wait for the kernel that waits for it.  So the reservation is made here, once
+// per context, before anything else runs.
+__global__ void reserve_local_memory_kernel(int* out, int n) {
+  int buf[64];  // (indexed dynamically: lives on the stack)
+  for (int i = 0; i < 64; ++i) buf[(i * n) & 63] = i;
+  if (out) out[0] = buf[(n + threadIdx.x) & 63];
+}
 }  // namespace
 
 namespace lmi {
@@ -453,6 +465,9 @@ int lm_ctx_create_on_stream(int device, void* cuda_stream, lm_ctx** out) {
   }
   int s = ensure(ctx, ctx->d_small, SMALL_BYTES);
   if (s < 0) { lm_ctx_destroy(ctx); return s; }
+  reserve_local_memory_kernel<<<1, 32, 0, ctx->stream>>>((int*)ctx->d_small.p, 1);
+  if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "reserve_local_memory_kernel");
+  if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "reserve_local_memory_kernel");
   for (auto& sl : ctx->slots) {
     if ((e = cudaEventCreate(&sl.ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&sl.ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -518,7 +533,7 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
     ctx->opt_class_cache = value;
     return LM_OK;
   }
-  if (option == LM_OPT_UPLOAD && value >= 0 && value <= 2) {
+  if (option == LM_OPT_UPLOAD && value >= 0 && value <= 3) {
     ctx->opt_upload = value;
     return LM_OK;
   }

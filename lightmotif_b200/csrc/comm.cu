@@ -28,6 +28,8 @@
 #include <new>
 #include <vector>
 
+#include <mutex>
+
 #include "internal.cuh"
 
 using namespace lm;
@@ -159,9 +161,33 @@ int comm_fail(lm_comm* c, cudaError_t e, const char* what) {
     if (_e != cudaSuccess) return comm_fail(comm, _e, #expr); \
   } while (0)
 
+// CUDA loads kernels lazily, at their first launch, and a load may synchronise with whatever runs on the
+// device.  A sharded scan keeps gather_wait_kernel spinning until every rank has published; if a rank that
+// shares the device (a communicator may list a device twice) then launches an instance nobody has launched
+// before -- e.g. the second scan of a matrix, re-planned for the maximum the first one found --, its load
+// waits for the kernel that waits for it (observed as the 30 s time-out).  Communicators therefore load every
+// scan kernel up front, once per device and process.
+int preload_kernels(lm_comm* comm, int device) {
+  static std::mutex mu;
+  static std::vector<int> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (std::find(done.begin(), done.end(), device) != done.end()) return LM_OK;
+  CM_TRY(cudaSetDevice(device));
+  CM_TRY(lm::preload_prune_kernels());
+  CM_TRY(lm::preload_score_kernels());
+  cudaFuncAttributes at;
+  CM_TRY(cudaFuncGetAttributes(&at, publish_kernel));
+  CM_TRY(cudaFuncGetAttributes(&at, gather_wait_kernel));
+  CM_TRY(cudaFuncGetAttributes(&at, ack_kernel));
+  CM_TRY(cudaFuncGetAttributes(&at, ack_wait_kernel));
+  done.push_back(device);
+  return LM_OK;
+}
+
 int alloc_local(lm_comm* comm, int li) {
   lm_comm::Local& L = comm->local[li];
   CM_TRY(cudaSetDevice(L.ctx->device));
+  LM_CHECK(preload_kernels(comm, L.ctx->device));
   const size_t bytes = xbuf_bytes(comm->hcap);
   CM_TRY(cudaMalloc((void**)&L.xbuf, bytes));  // plain cudaMalloc: exportable with cudaIpcGetMemHandle
   CM_TRY(cudaMemset(L.xbuf, 0, XOFF_HITS));

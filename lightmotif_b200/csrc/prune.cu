@@ -1261,6 +1261,41 @@ ProteinPlan plan_prune_protein(const float* pssm, size_t m, size_t stride, doubl
 
 int prune_slice_positions() { return WARP_ROWS * 32; }
 
+// Load every instance of the filter kernel now (CUDA loads kernels lazily, at their first launch, and a load
+// may synchronise with the kernels running on the device: see lmi::preload_kernels in capi.cu).
+namespace {
+template <int RR, bool PP>
+cudaError_t preload_instances() {
+  cudaFuncAttributes at;
+  cudaError_t e = cudaSuccess;
+#ifdef LM_PRUNE_ONLY
+  if (RR == 6 && PP) e = cudaFuncGetAttributes(&at, prune_kernel<6, true, false, false, false>);
+#else
+#define LM_LOAD(THR, BATCH, DENSE) \
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, prune_kernel<RR, PP, THR, BATCH, DENSE>);
+  LM_LOAD(false, true, false) LM_LOAD(false, false, true) LM_LOAD(false, false, false)
+  LM_LOAD(true, true, false) LM_LOAD(true, false, true) LM_LOAD(true, false, false)
+#undef LM_LOAD
+#endif
+  return e;
+}
+}  // namespace
+
+cudaError_t preload_prune_kernels() {
+  cudaError_t e = preload_instances<3, true>();
+  if (e == cudaSuccess) e = preload_instances<4, true>();
+  if (e == cudaSuccess) e = preload_instances<5, true>();
+  if (e == cudaSuccess) e = preload_instances<6, true>();
+  if (e == cudaSuccess) e = preload_instances<8, true>();
+  if (e == cudaSuccess) e = preload_instances<4, false>();
+  if (e == cudaSuccess) e = preload_instances<6, false>();
+  if (e == cudaSuccess) e = preload_instances<8, false>();
+  if (e == cudaSuccess) e = preload_instances<10, false>();
+  if (e == cudaSuccess) e = preload_instances<12, false>();
+  if (e == cudaSuccess) e = preload_instances<16, false>();
+  return e;
+}
+
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream) {
   return threshold_mode ? launch_r<true>(a, sm_count, stream) : launch_r<false>(a, sm_count, stream);
 }

@@ -123,5 +123,6 @@ struct PruneArgs {
 cudaError_t launch_prune(bool threshold_mode, const PruneArgs& a, int sm_count, cudaStream_t stream);
 // positions one consumer warp filters at a time (the granularity of the recheck queue)
 int prune_slice_positions();
+cudaError_t preload_prune_kernels();  // load every kernel instance now instead of at its first launch
 
 }  // namespace lm

@@ -426,6 +426,27 @@ cudaError_t launch_mode(int mode, const ScoreArgs& a, int sm_count, cudaStream_t
 
 }  // namespace
 
+namespace {
+template <int KP, bool U8>
+cudaError_t preload_modes() {
+  cudaFuncAttributes at;
+  cudaError_t e = cudaSuccess;
+#define LM_CASE(M) if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, score_kernel<KP, M, U8>);
+  LM_CASE(1) LM_CASE(2) LM_CASE(3) LM_CASE(4) LM_CASE(5) LM_CASE(6) LM_CASE(7)
+#undef LM_CASE
+  return e;
+}
+}  // namespace
+
+// load every instance now instead of at its first launch (see lmi::preload_kernels in capi.cu)
+cudaError_t preload_score_kernels() {
+  cudaError_t e = preload_modes<16, false>();
+  if (e == cudaSuccess) e = preload_modes<16, true>();
+  if (e == cudaSuccess) e = preload_modes<32, false>();
+  if (e == cudaSuccess) e = preload_modes<32, true>();
+  return e;
+}
+
 cudaError_t launch_score(int alphabet, int mode, bool is_u8, const ScoreArgs& a, int sm_count,
                          cudaStream_t stream) {
   if (alphabet == LM_DNA)

@@ -53,6 +53,7 @@ struct ScoreArgs {
 // Enqueue the scoring kernel on `stream`.  is_u8 selects the saturating u8
 // pipeline (tables hold u32-expanded DiscreteMatrix cells).  Returns a CUDA
 // error code.
+cudaError_t preload_score_kernels();
 cudaError_t launch_score(int alphabet, int mode, bool is_u8, const ScoreArgs& a, int sm_count,
                          cudaStream_t stream);
 

@@ -4,12 +4,13 @@
 // several TB/s, so a call that starts from a HOST matrix is bound by PCIe (~55 GB/s here), not by the
 // scan.  DNA symbols other than N need 2 bits, so the upload is done from BOTH ends of the matrix at once:
 //
-//   front   the copy engine pulls chunks of the caller's (pinned) matrix as they are       1 B / symbol
+//   front   whenever the link would be idle, the copy engine pulls a chunk of the caller's
+//           (pinned) matrix as it is                                                      1 B / symbol
 //   back    host threads pack chunks 4 symbols per byte (hostpack.cpp) into a ring of
 //           pinned slots; each goes over PCIe packed and unpack2_kernel expands it into
 //           its place in the device matrix                                                0.25 B / symbol
 //
-// until the two ends meet: the copy engine is never idle, the host threads add what they can, and the
+// until the two ends meet: the link is never idle, packed chunks never wait behind plain ones, and the
 // split adapts to the machine (host cores, memory bandwidth, other ranks on the same host).  A chunk
 // that holds a symbol > 3 (N) is sent as it is.  The device matrix is byte-identical to a plain copy
 // (tests/test_gpu_parity.py::test_packed_upload_*).  Pageable source buffers go through the packed path
@@ -30,7 +31,7 @@ bool pack2(const uint8_t* src, size_t n, uint8_t* dst);  // hostpack.cpp
 
 namespace {
 
-constexpr size_t CHUNK = 8u << 20;        // symbols (= bytes of the matrix) per chunk
+constexpr size_t CHUNK = 4u << 20;        // symbols (= bytes of the matrix) per chunk
 constexpr size_t SLOT = CHUNK / 4;        // packed bytes per chunk
 constexpr int RAW_DEPTH = 2;              // plain copies kept in flight
 constexpr int MAX_THREADS = 64;
@@ -101,7 +102,7 @@ int upload_threads(const lm_ctx* ctx) {
 }
 
 int get_uploader(lm_ctx* ctx, int threads, lm_uploader** out) {
-  const int want = threads + 4;
+  const int want = 2 * threads + 8;  // (a packed chunk may wait behind plain ones: spare slots keep the packers busy)
   if (ctx->uploader && ctx->uploader->nslots >= want) { *out = ctx->uploader; return LM_OK; }
   free_uploader(ctx->uploader);
   ctx->uploader = nullptr;
@@ -142,6 +143,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
                       attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   const bool raw_front = pinned && ctx->opt_upload != 2;  // 2 = packed chunks only (tests, pageable sources)
+  const bool raw_gaps_only = ctx->opt_upload == 3;       // 3 = plain chunks only while no packed copy is pending
   const int64_t nchunks = (int64_t)((bytes + CHUNK - 1) / CHUNK);
   auto chunk_len = [&](int64_t c) { return (size_t)c * CHUNK + CHUNK <= bytes ? CHUNK : bytes - (size_t)c * CHUNK; };
 
@@ -201,6 +203,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
     ++n_raw;
   };
   int64_t issued = 0;
+  int last_packed = -1;  // slot of the packed chunk issued last
   while (issued < nchunks && err == cudaSuccess) {
     // recycle what the device is done with
     while (!packed_inflight.empty() && cudaEventQuery(U->slot_ev[packed_inflight.front()]) == cudaSuccess) {
@@ -216,6 +219,11 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
       --raw_inflight;
     }
     cudaGetLastError();  // (cudaErrorNotReady of the queries)
+    // plain chunks only fill the gaps of the link: a packed chunk carries four times the symbols per byte,
+    // so it must never queue behind plain ones (measured: with plain copies always in flight the upload
+    // was slower than with packed chunks alone)
+    const bool packed_copy_pending = last_packed >= 0 && cudaEventQuery(U->copy_ev[last_packed]) != cudaSuccess;
+    cudaGetLastError();
     Ready r{-1, 0, false};
     int64_t raw_chunk = -1;
     bool exhausted = false;
@@ -224,7 +232,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
       if (!ready.empty()) {
         r = ready.front();
         ready.pop_front();
-      } else if (raw_front && raw_inflight < RAW_DEPTH && front < back) {
+      } else if (raw_front && raw_inflight < RAW_DEPTH && front < back && !(raw_gaps_only && packed_copy_pending)) {
         raw_chunk = front++;
         exhausted = front >= back;
       }
@@ -245,6 +253,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
         }
         if (err == cudaSuccess) err = cudaEventRecord(U->slot_ev[r.slot], U->s_pack);
         packed_inflight.push_back(r.slot);
+        last_packed = r.slot;
         pcie += len / 4;
         ++n_packed;
       } else {  // holds N (or anything else that is not 0..3): sent as it is
