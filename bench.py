@@ -613,7 +613,7 @@ def run_ours(args):
                "d2h_bytes_per_step": 272 if world == 1 else (320 + 320 * world + 8) * world,
                "steps": n_e2e,
                "host_matrix_bytes_per_step": int(harr.nbytes) * world,
-               "upload": {"how": "lm_seq_from_striped, LM_OPT_UPLOAD=1: the copy engine fills the gaps of the link with plain 4 MiB chunks from the front of the "
+               "upload": {"how": "lm_seq_from_striped, LM_OPT_UPLOAD=1: the copy engine pulls plain 4 MiB chunks from the front of the "
                                  "pinned matrix while host threads pack chunks from its back 4 symbols per byte; a kernel expands them "
                                  "in place (device matrix byte-identical, tests/test_gpu_parity.py::test_packed_upload_*)",
                           "host_threads_per_rank": up["threads"], "packed_chunks_rank0": up["packed_chunks"],
