@@ -20,6 +20,10 @@
 using namespace lm;
 using namespace lmi;
 
+#ifndef LM_BATCH_BOOT
+#define LM_BATCH_BOOT 4096  // rows scored exactly to seed the running maxima of a many-motif argmax call
+#endif
+
 namespace {
 constexpr size_t SLACK_ROWS = 64;      // readable rows kept behind rows + wrap
 constexpr size_t SMALL_BYTES = 1 << 20;  // keys / counters block
@@ -1568,9 +1572,10 @@ int batch_launch(lm_ctx* ctx, const lm_seq* seq, lm_batch_cache& B, bool argmax_
   uint64_t launches = 0, n_pruned = 0;
   LM_TRY(cudaMemsetAsync(blocks, 0, n * BATCH_BLOCK + 1024, ctx->stream));
   // rows scored exactly first to seed the running maxima of the filtered argmax scans
-  // (8192 rows measured best for 1 024 motifs x 100 Mbp: 4096 / 2048 / 1024 rows cost +1.9 / +4.1 / +6.6 ms per call --
-  // the first few hundred tiles of every motif are filtered at the seed, by the whole grid at once)
-  const size_t boot = argmax_mode ? std::min<size_t>(n_rows, 8192) : 0;
+  // (with motif-major work items the seed mattered: 8192 / 4096 / 2048 rows gave 30.1 / 32.0 / 34.2 ms per call of
+  // config 2, because the whole grid started every motif at once; with interleaved motifs -- prune.cu BATCH_ILV --
+  // 27.8 / 27.7 / 28.0 ms)
+  const size_t boot = argmax_mode ? std::min<size_t>(n_rows, LM_BATCH_BOOT) : 0;
   bool any_pruned = false;
   for (const auto& it : B.items) any_pruned = any_pruned || (it.pruned && seq->length >= it.m);
   if (argmax_mode && any_pruned && boot) {

@@ -77,6 +77,10 @@ constexpr int PTILE_ROWS = SPT * WARP_ROWS;
 constexpr int CLAIM = PW / SPT > 0 ? PW / SPT : 1;  // consecutive tiles a producer claims per trip to the global counter
 static_assert(NSTAGE * SPT > PW + SPT - 1 || NSTAGE * SPT >= 2 * PW, "ring too shallow for the slices in flight");
 constexpr int QCAP = 128;               // queue entries (quads) per warp and tile; more => exact fallback
+#ifndef LM_PRUNE_ILV
+#define LM_PRUNE_ILV 12
+#endif
+constexpr int BATCH_ILV = LM_PRUNE_ILV;  // motifs whose work items are interleaved in a many-motif launch
 static_assert(PL % 2 == 1, "PL must be odd (bank-conflict-free row groups)");
 
 // What a consumer warp needs to know about the tile in a stage.  Everything that depends on the
@@ -351,9 +355,21 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
         item = __shfl_sync(0xffffffffu, item, 0);
         claim_base = item;
       }
-      const uint32_t mq = a.n_batch > 1 ? (uint32_t)(item / num_tiles) : 0u;
-      const unsigned long long tile = a.n_batch > 1 ? item - (unsigned long long)mq * num_tiles
-                                                    : item;
+      // Many motifs: the items of BATCH_ILV motifs are interleaved (tile-major within the block of motifs), so a
+      // motif's sweep starts with grid / BATCH_ILV CTAs instead of the whole grid.  Every tile in flight when a
+      // motif starts is filtered at the seed of its running maximum: with motif-major order that was the first
+      // ~900 of a 3 150-tile sweep (config 2), and the seed's quality showed in the run time.  BATCH_ILV divides the
+      // usual grid (444), so a CTA tends to stay with one motif and its tables stay in place.
+      uint32_t mq = 0;
+      unsigned long long tile = item;
+      if (a.n_batch > 1) {
+        const unsigned long long per_block = (unsigned long long)BATCH_ILV * num_tiles;
+        const unsigned long long blk = item / per_block, r = item - blk * per_block;
+        const uint32_t left = a.n_batch - (uint32_t)blk * BATCH_ILV;  // motifs in this block (the last one may be short)
+        const uint32_t gb = left < (uint32_t)BATCH_ILV ? left : (uint32_t)BATCH_ILV;
+        mq = (uint32_t)blk * BATCH_ILV + (uint32_t)(r % gb);
+        tile = r / gb;
+      }
       const bool live = item < total_items;
       if (live && mq != cur_mq) {  // (warp-uniform) next motif: its plan, tables and result block
         const BatchMotif* src = a.batch ? &a.batch[mq] : &a.one;
