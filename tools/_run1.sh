@@ -1,1 +1,4 @@
-for v in ilv12 b4096 b2048 b1024; do echo "$v"; LM_B200_LIB=tools/_variants/lib_$v.so timeout 300 python tools/config2_bench.py 2>&1 | tail -1 | cut -c100-230; done
+mkdir -p gpurun_out
+timeout 300 python tools/stripe_bench.py 2>&1 | tail -1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stripe_kernel -s 1 -c 1 -f -o gpurun_out/stripe_r02d python tools/stripe_bench.py > gpurun_out/ncu_stripe_r02d.log 2>&1
+tail -1 gpurun_out/ncu_stripe_r02d.log
