@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-timeout 300 python tools/stripe_bench.py 2>&1 | tail -1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stripe_kernel -s 1 -c 1 -f -o gpurun_out/stripe_r02d python tools/stripe_bench.py > gpurun_out/ncu_stripe_r02d.log 2>&1
-tail -1 gpurun_out/ncu_stripe_r02d.log
+bash tools/gpu_round.sh r02_final
+timeout 300 python tools/upload_bench.py --gb 5 --threads 15 --reps 5 > gpurun_out/upload_r02_final.txt 2>&1; tail -5 gpurun_out/upload_r02_final.txt
