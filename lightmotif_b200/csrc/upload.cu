@@ -22,6 +22,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include "internal.cuh"
 
@@ -95,7 +98,15 @@ namespace {
 int upload_threads(const lm_ctx* ctx) {
   int t = ctx->opt_upload_threads;
   if (t <= 0) {
-    const unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = std::thread::hardware_concurrency();
+#if defined(__linux__)
+    cpu_set_t set;  // (a process confined to fewer CPUs -- taskset, cpusets, one rank of many -- must not oversubscribe
+    CPU_ZERO(&set);  //  them: twice as many packing threads as cores measured slower than the plain copy)
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+      const unsigned allowed = (unsigned)CPU_COUNT(&set);
+      if (allowed && (hw == 0 || allowed < hw)) hw = allowed;
+    }
+#endif
     t = hw > 2 ? (int)hw - 1 : 1;  // one core is left to the thread that feeds the copy engine
   }
   return t > MAX_THREADS ? MAX_THREADS : t;
@@ -183,7 +194,11 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
   };
   std::vector<std::thread> pool;
   pool.reserve(threads);
-  for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+  try {
+    for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+  } catch (...) {  // (thread limit of the process: carry on with the threads that did start -- the copy engine takes
+  }                //  whatever they do not; nothing may unwind across the C ABI)
+  const bool no_packers = pool.empty();
 
   cudaError_t err = cudaSuccess;
   uint64_t pcie = 0, n_packed = 0, n_raw = 0;
@@ -232,7 +247,8 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
       if (!ready.empty()) {
         r = ready.front();
         ready.pop_front();
-      } else if (raw_front && raw_inflight < RAW_DEPTH && front < back && !(raw_gaps_only && packed_copy_pending)) {
+      } else if ((raw_front || no_packers) && raw_inflight < RAW_DEPTH && front < back &&
+                 !(raw_gaps_only && packed_copy_pending && !no_packers)) {
         raw_chunk = front++;
         exhausted = front >= back;
       }
