@@ -94,4 +94,18 @@ assert [(h["row"], h["col"]) for h in sh] == list(zip(ro.tolist(), co.tolist()))
 for sl in slabs:
     sl.free()
 comm.close()
+# packed upload (host threads pack 2-bit chunks, unpack2_kernel expands them; the chunk holding N goes plain) and
+# the exact kernel's prefix-table path (tiles without N)
+a = np.random.default_rng(3).integers(0, 4, size=((9 << 20) // 32 + 19, 32), dtype=np.uint8)
+a[5, 5] = 4
+for mode in (1, 2):
+    dna.set_upload(mode, threads=2, min_bytes=0)
+    up = dna.sequence_from_striped(a, (a.shape[0] - 19) * 32, 19)
+    assert np.array_equal(up.download(), a)
+    up.free()
+dna.set_upload(1, 0, 64 << 20)
+clean = O.synth_dna(100_003)
+cseq = dna.sequence_from_symbols(clean, 19)
+cst = O.stripe(O.DNA, clean, 32, 19)
+assert np.array_equal(cseq.score(pssm).view(np.uint32), O.score_f32(pssm, cst, clean.size).view(np.uint32))
 print("sanitize smoke ok", best, e)

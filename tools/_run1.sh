@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_compat.py tests/test_cpp_mirror.py -m gpu -x -q 2>&1 | tail -3
-timeout 120 python tools/kbench.py --bp 1000000000 --reps 5 --prune 0 --tag exact_prefix 2>&1 | tail -1 | cut -c1-110
-timeout 120 python tools/kbench.py --bp 1000000000 --reps 5 --prune 0 --m 12 --tag exact_m12 2>&1 | tail -1 | cut -c1-110
-timeout 120 python tools/kbench.py --bp 1000000000 --reps 5 --prune 0 --m 32 --tag exact_m32 2>&1 | tail -1 | cut -c1-110
+mkdir -p gpurun_out
+timeout 300 python tests/sanitize_smoke.py 2>&1 | tail -2 | cut -c1-200
+timeout 900 compute-sanitizer --tool memcheck python tests/sanitize_smoke.py > gpurun_out/memcheck_r02f.log 2>&1; grep -E "ERROR SUMMARY|sanitize smoke" gpurun_out/memcheck_r02f.log | cut -c1-160
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python tests/sanitize_smoke.py > gpurun_out/racecheck_r02f.log 2>&1; grep -E "RACECHECK SUMMARY|sanitize smoke" gpurun_out/racecheck_r02f.log | cut -c1-160
+timeout 600 compute-sanitizer --tool synccheck python tests/sanitize_smoke.py > gpurun_out/synccheck_r02f.log 2>&1; grep -E "ERROR SUMMARY|sanitize smoke" gpurun_out/synccheck_r02f.log | cut -c1-160
