@@ -637,11 +637,12 @@ __global__ void __launch_bounds__(PT, LM_PRUNE_MINBLOCKS) prune_kernel(const Pru
       // The adds are IMADs (`p * 1 + acc`, FMA pipe) beside the PRMTs on the ALU pipe.  NP3 PAIRS of look-ups are
       // instead summed by one 3-input add (IADD3, ALU pipe): two issue slots fewer per pair, one more ALU-pipe
       // instruction.  Measured on the headline instance (paired R = 6): one pair +1.4 %, two -1 %, three -4 %
-      // (the ALU pipe becomes the limiter); other instances keep NP3 = 0 (not measured).
+      // (the ALU pipe becomes the limiter); one pair in every many-motif instance: config 2 -2.3 %; the other
+      // single-motif instances measured within +-1 % either way and keep NP3 = 0.
 #ifdef LM_PRUNE_ADD3
       constexpr int NP3 = (LM_PRUNE_ADD3 < R / 2 ? LM_PRUNE_ADD3 : R / 2);
 #else
-      constexpr int NP3 = (PAIR && R == 6 && !BATCH && !DENSE) ? 1 : 0;
+      constexpr int NP3 = (BATCH || (PAIR && R == 6 && !DENSE)) ? 1 : 0;
 #endif
 #pragma unroll
       for (int kp = 0; kp < NP3; ++kp) {
