@@ -135,8 +135,8 @@ float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
  * sequence and reuse it while sequence and class map are unchanged, 0 = rebuild
  * it on every call */
 #define LM_OPT_CLASS_CACHE 6
-/* lm_seq_from_striped[_slab] of a large DNA matrix (pinned or pageable host
- * memory): 1 (default) = host threads pack chunks from the back of the matrix
+/* lm_seq_from_striped[_slab] / lm_seq_from_symbols of a large DNA matrix or
+ * symbol array (pinned or pageable host memory): 1 (default) = host threads pack chunks from the back of the matrix
  * 4 symbols per byte (chunks holding N go as they are), a kernel expands them
  * in place, and the copy engine pulls plain chunks from the front meanwhile --
  * the device matrix is byte-identical, the call is no longer bound by
@@ -148,7 +148,7 @@ float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
 /* matrices smaller than this many bytes take the plain copy (default 64 MiB) */
 #define LM_OPT_UPLOAD_MIN_BYTES 9
 int lm_ctx_set_option(lm_ctx *ctx, int option, int value);
-/* the most recent lm_seq_from_striped[_slab]: out[0] = bytes that crossed PCIe,
+/* the most recent lm_seq_from_striped[_slab] / lm_seq_from_symbols: out[0] = bytes that crossed PCIe,
  * out[1] = chunks sent packed, out[2] = chunks sent plain, out[3] = host
  * threads used (0: plain copy) */
 int lm_ctx_last_upload(const lm_ctx *ctx, uint64_t out[4]);

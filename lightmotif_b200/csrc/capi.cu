@@ -833,7 +833,13 @@ static int seq_from_flat(lm_ctx* ctx, int alphabet, const uint8_t* src, size_t n
     if ((st = ensure(ctx, ctx->d_in, n + 16)) < 0) break;  // the stripe kernel reads whole 4-byte words
     unsigned long long* d_bad = (unsigned long long*)ctx->d_small.p;
     cudaError_t e = cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream);
-    if (e == cudaSuccess && n) e = cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n) {
+      if (!from_ascii && upload_wants_packed(ctx, alphabet, 32, n)) {  // encoded DNA symbols: partly 2-bit packed (upload.cu)
+        if ((st = upload_striped_dna(ctx, (uint8_t*)ctx->d_in.p, src, n)) < 0) break;
+      } else {
+        e = cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
+      }
+    }
     if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t*)ctx->d_in.p + n, 0, 16, ctx->stream);  // last word past n
     if (e != cudaSuccess) { st = fail(ctx, e, "upload"); break; }
     timer_begin(ctx);

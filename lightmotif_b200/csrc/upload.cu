@@ -143,9 +143,16 @@ bool upload_wants_packed(const lm_ctx* ctx, int alphabet, size_t stride, size_t 
   return ctx->opt_upload != 0 && alphabet == LM_DNA && stride == 32 && bytes >= (size_t)ctx->opt_upload_min_bytes;
 }
 
-// Copy `bytes` (a multiple of 32) of a host striped DNA matrix to `dst` (device, 256-byte aligned, allocated
-// in order on ctx->stream).  On return the copies are ordered before later work on ctx->stream.
-int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t bytes) {
+// Copy `bytes` DNA symbols (a striped matrix, or the flat symbols of lm_seq_from_symbols) from host memory to
+// `dst` (device, 16-byte aligned, allocated before or in order on ctx->stream).  A tail of fewer than 64 bytes is
+// copied as it is.  On return the copies are ordered before later work on ctx->stream.
+int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t bytes_all) {
+  const size_t bytes = bytes_all & ~(size_t)63;  // whole 16-symbol words of the expansion kernel, 4 per packed word
+  if (bytes_all > bytes) {
+    cudaError_t e = cudaMemcpyAsync(dst + bytes, src + bytes, bytes_all - bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, e, "packed upload: tail");
+  }
+  if (bytes == 0) return LM_OK;
   const int threads = upload_threads(ctx);
   lm_uploader* U = nullptr;
   LM_CHECK(get_uploader(ctx, threads, &U));
@@ -163,6 +170,10 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
   LM_TRY(cudaStreamWaitEvent(U->s_raw, U->ev_begin, 0));
   LM_TRY(cudaStreamWaitEvent(U->s_pack, U->ev_begin, 0));
 
+  const bool dbg = getenv("LM_UPLOAD_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  std::atomic<long long> wait_us{0};
   struct Ready { int64_t chunk; int slot; bool ok; };
   std::mutex mu;
   std::condition_variable cv_ready, cv_free;
@@ -178,7 +189,9 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
       int slot;
       {
         std::unique_lock<std::mutex> l(mu);
+        const double w0 = dbg ? now() : 0.0;
         cv_free.wait(l, [&] { return stop || back <= front || !free_slots.empty(); });
+        if (dbg) wait_us += (long long)((now() - w0) * 1000.0);
         if (stop || back <= front) return;
         c = --back;
         slot = free_slots.front();
@@ -298,7 +311,15 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
     stop = true;
   }
   cv_free.notify_all();
+  const double t_issued = now();
   for (auto& t : pool) t.join();
+  if (dbg) {
+    cudaStreamSynchronize(U->s_raw);
+    cudaStreamSynchronize(U->s_pack);
+    fprintf(stderr, "[upload] %.1f MB: spawn+issue %.2f ms, drain %.2f ms, workers waited for slots %.2f ms in total (%d threads), packed %llu plain %llu\n",
+            bytes / 1e6, t_issued - t_begin, now() - t_issued, wait_us.load() / 1000.0, threads, (unsigned long long)n_packed,
+            (unsigned long long)n_raw);
+  }
   if (err == cudaSuccess) err = cudaEventRecord(U->ev_raw, U->s_raw);
   if (err == cudaSuccess) err = cudaEventRecord(U->ev_pack, U->s_pack);
   if (err == cudaSuccess) err = cudaStreamWaitEvent(ctx->stream, U->ev_raw, 0);
@@ -308,7 +329,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
     cudaStreamSynchronize(U->s_pack);
     return fail(ctx, err, "packed upload");
   }
-  ctx->upload_stats[0] = pcie;
+  ctx->upload_stats[0] = pcie + (bytes_all - bytes);
   ctx->upload_stats[1] = n_packed;
   ctx->upload_stats[2] = n_raw;
   ctx->upload_stats[3] = (uint64_t)threads;

@@ -530,3 +530,26 @@ def test_packed_upload_scan_equals_plain(lm, dna, jaspar):
             dna.set_upload(1, 0, 64 << 20)
     assert res[0] == res[1] == res[2]
     assert res[0][0] is not None
+
+
+def test_packed_upload_of_flat_symbols(lm, dna):
+    """lm_seq_from_symbols of a long encoded DNA sequence travels through the same two-ended upload (ragged
+    length, N inside, unaligned tail) and is striped on the device exactly as before."""
+    rng = np.random.default_rng(21)
+    n = (13 << 20) + 37
+    sym = rng.integers(0, 4, n, dtype=np.uint8)
+    sym[5_000_000:5_000_300] = 4
+    sym[-1] = 4
+    want = O.stripe(O.DNA, sym, 32, 9)
+    for mode in (0, 1, 2):
+        dna.set_upload(mode, threads=3, min_bytes=0)
+        try:
+            seq = dna.sequence_from_symbols(sym, 9)
+            got = seq.download()
+            up = dna.last_upload
+            seq.free()
+        finally:
+            dna.set_upload(1, 0, 64 << 20)
+        assert np.array_equal(got, want), mode
+        if mode:
+            assert up["packed_chunks"] >= 1 and up["pcie_bytes"] < n
