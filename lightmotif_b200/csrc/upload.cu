@@ -14,7 +14,8 @@
 // split adapts to the machine (host cores, memory bandwidth, other ranks on the same host).  A chunk
 // that holds a symbol > 3 (N) is sent as it is.  The device matrix is byte-identical to a plain copy
 // (tests/test_gpu_parity.py::test_packed_upload_*).  Pageable source buffers go through the packed path
-// only (the ring is the pinned staging a plain copy would need anyway).
+// only (the ring is the pinned staging a plain copy would need anyway).  LM_UPLOAD_DEBUG=1 in the environment
+// prints one timing line per upload to stderr.
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -247,9 +248,9 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
       --raw_inflight;
     }
     cudaGetLastError();  // (cudaErrorNotReady of the queries)
-    // plain chunks only fill the gaps of the link: a packed chunk carries four times the symbols per byte,
-    // so it must never queue behind plain ones (measured: with plain copies always in flight the upload
-    // was slower than with packed chunks alone)
+    // (policy 3 only: plain chunks are issued only while no packed copy is pending, so that a packed chunk --
+    // four times the symbols per byte -- never queues behind plain ones.  Measured equal to policies 1 and 2 on
+    // a 16-thread host, where the packing threads, not the link, are the limit.)
     const bool packed_copy_pending = last_packed >= 0 && cudaEventQuery(U->copy_ev[last_packed]) != cudaSuccess;
     cudaGetLastError();
     Ready r{-1, 0, false};
