@@ -469,6 +469,13 @@ int lm_ctx_create_on_stream(int device, void* cuda_stream, lm_ctx** out) {
   }
   int s = ensure(ctx, ctx->d_small, SMALL_BYTES);
   if (s < 0) { lm_ctx_destroy(ctx); return s; }
+  // (the per-motif tables never regrow in steady state: a cudaFree synchronises the device -- see the note on
+  // reserve_local_memory_kernel -- and the largest motif the kernels accept needs < 128 KB)
+  if ((s = ensure(ctx, ctx->d_table, 128 << 10)) < 0 || (s = ensure(ctx, ctx->d_table2, 128 << 10)) < 0 ||
+      (s = ensure_pinned(ctx, 128 << 10)) < 0) {
+    lm_ctx_destroy(ctx);
+    return s;
+  }
   reserve_local_memory_kernel<<<1, 32, 0, ctx->stream>>>((int*)ctx->d_small.p, 1);
   if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "reserve_local_memory_kernel");
   if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "reserve_local_memory_kernel");
