@@ -585,7 +585,7 @@ def run_ours(args):
 
         def e2e_run(mode, threads):
             pli.set_upload(mode, threads)
-            for _ in range(min(args.warmup, 2)):
+            for _ in range(2):  # (mode 1 times its first upload two-ended and its second plain, then keeps the faster)
                 e2e_step()
             sync_all()
             n = max(3, min(args.steps, 5))
@@ -613,10 +613,12 @@ def run_ours(args):
                "d2h_bytes_per_step": 272 if world == 1 else (320 + 320 * world + 8) * world,
                "steps": n_e2e,
                "host_matrix_bytes_per_step": int(harr.nbytes) * world,
-               "upload": {"how": "lm_seq_from_striped, LM_OPT_UPLOAD=1: the copy engine pulls plain 4 MiB chunks from the front of the "
+               "upload": {"how": "lm_seq_from_striped, LM_OPT_UPLOAD=1 (adaptive: the context timed one upload two-ended and one plain during the warm-up "
+                                 "and keeps the faster -- `chosen`). Two-ended: the copy engine pulls plain 4 MiB chunks from the front of the "
                                  "pinned matrix while host threads pack chunks from its back 4 symbols per byte; a kernel expands them "
                                  "in place (device matrix byte-identical, tests/test_gpu_parity.py::test_packed_upload_*)",
-                          "host_threads_per_rank": up["threads"], "packed_chunks_rank0": up["packed_chunks"],
+                          "chosen": "two-ended" if up["threads"] else "plain copy",
+                          "host_threads_per_rank": up_threads, "packed_chunks_rank0": up["packed_chunks"],
                           "plain_chunks_rank0": up["plain_chunks"]},
                "plain_copy": {"value": plain_gbps, "unit": "Gbp/s", "note": "LM_OPT_UPLOAD=0: the whole matrix as one 1 B/symbol copy (round 1's path)"},
                "api": ("lm_seq_from_striped(pinned host StripedSequence) + lm_seq_score_argmax_f32" if world == 1 else

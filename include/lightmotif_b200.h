@@ -136,12 +136,17 @@ float lm_ctx_last_sm_clock_mhz(const lm_ctx *ctx);
  * it on every call */
 #define LM_OPT_CLASS_CACHE 6
 /* lm_seq_from_striped[_slab] / lm_seq_from_symbols of a large DNA matrix or
- * symbol array (pinned or pageable host memory): 1 (default) = host threads pack chunks from the back of the matrix
- * 4 symbols per byte (chunks holding N go as they are), a kernel expands them
- * in place, and the copy engine pulls plain chunks from the front meanwhile --
- * the device matrix is byte-identical, the call is no longer bound by
- * 1 B/symbol over PCIe; 0 = plain copy; 2 = packed chunks only; 3 = as 1, but
- * plain chunks only while no packed copy is pending. */
+ * symbol array (pinned or pageable host memory).  Two-ended upload: host
+ * threads pack chunks from the back of the matrix 4 symbols per byte (chunks
+ * holding N go as they are), a kernel expands them in place, and the copy
+ * engine pulls plain chunks from the front meanwhile -- the device matrix is
+ * byte-identical, the call is no longer bound by 1 B/symbol over PCIe.
+ * 1 (default) = adaptive: the context times its large uploads both ways (the
+ * first two-ended, the second plain) and keeps the faster one, re-trying the
+ * other every 32nd upload -- several ranks sharing one host can saturate its
+ * memory with plain copies alone; 0 = always the plain copy; 2 = packed chunks
+ * only; 3 = two-ended, plain chunks only while no packed copy is pending;
+ * 4 = always two-ended. */
 #define LM_OPT_UPLOAD 7
 /* host threads that pack (0 = default: all hardware threads but one) */
 #define LM_OPT_UPLOAD_THREADS 8

@@ -402,7 +402,8 @@ class Pipeline:
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 2, int(rows)))
 
     def set_upload(self, mode=1, threads=0, min_bytes=None):
-        """LM_OPT_UPLOAD (0 plain copy, 1 plain + packed chunks, 2 packed chunks only), LM_OPT_UPLOAD_THREADS
+        """LM_OPT_UPLOAD (0 plain copy, 1 adaptive: times both ways and keeps the faster, 2 packed chunks only,
+        3 / 4 two-ended with plain chunks only in link gaps / always), LM_OPT_UPLOAD_THREADS
         (0 = all hardware threads but one), LM_OPT_UPLOAD_MIN_BYTES: how sequence_from_striped moves a large
         DNA matrix to the device."""
         self._check(capi.lib().lm_ctx_set_option(self._ctx, 7, int(mode)))

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -544,8 +545,10 @@ int lm_ctx_set_option(lm_ctx* ctx, int option, int value) {
     ctx->opt_class_cache = value;
     return LM_OK;
   }
-  if (option == LM_OPT_UPLOAD && value >= 0 && value <= 3) {
+  if (option == LM_OPT_UPLOAD && value >= 0 && value <= 4) {
     ctx->opt_upload = value;
+    ctx->upload_rate_packed = ctx->upload_rate_plain = 0.0;  // (measure again)
+    ctx->upload_calls = 0;
     return LM_OK;
   }
   if (option == LM_OPT_UPLOAD_THREADS && value >= 0) {
@@ -841,7 +844,7 @@ static int seq_from_flat(lm_ctx* ctx, int alphabet, const uint8_t* src, size_t n
     unsigned long long* d_bad = (unsigned long long*)ctx->d_small.p;
     cudaError_t e = cudaMemsetAsync(d_bad, 0xFF, 8, ctx->stream);
     if (e == cudaSuccess && n) {
-      if (!from_ascii && upload_wants_packed(ctx, alphabet, 32, n)) {  // encoded DNA symbols: partly 2-bit packed (upload.cu)
+      if (!from_ascii && upload_wants_packed(ctx, alphabet, 32, n, src)) {  // encoded DNA symbols: partly 2-bit packed (upload.cu)
         if ((st = upload_striped_dna(ctx, (uint8_t*)ctx->d_in.p, src, n)) < 0) break;
       } else {
         e = cudaMemcpyAsync(ctx->d_in.p, src, n, cudaMemcpyHostToDevice, ctx->stream);
@@ -889,9 +892,13 @@ int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t r
   lm_seq* s = nullptr;
   LM_CHECK(seq_alloc(ctx, alphabet, rows, wrap, length, &s));
   cudaError_t e = cudaSuccess;
-  if (upload_wants_packed(ctx, alphabet, stride, (rows + wrap) * 32)) {
+  const size_t nbytes = (rows + wrap) * 32;
+  const bool large = alphabet == LM_DNA && stride == 32 && nbytes >= (size_t)ctx->opt_upload_min_bytes;
+  const bool packed = upload_wants_packed(ctx, alphabet, stride, nbytes, data);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (packed) {
     // large DNA matrix: plain copy from the front, 2-bit packed chunks from the back (upload.cu)
-    int st = upload_striped_dna(ctx, s->data, data, (rows + wrap) * 32);
+    int st = upload_striped_dna(ctx, s->data, data, nbytes);
     if (st < 0) { lm_seq_free(ctx, s); return st; }
   } else if (rows + wrap) {
     e = copy_rows(s->data, 32, data, stride, 32, rows + wrap, cudaMemcpyHostToDevice, ctx->stream);
@@ -902,6 +909,8 @@ int lm_seq_from_striped(lm_ctx* ctx, int alphabet, const uint8_t* data, size_t r
     e = cudaMemsetAsync(s->data + (rows + wrap) * 32, pad_symbol(alphabet), SLACK_ROWS * 32, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { int st = fail(ctx, e, "upload striped"); lm_seq_free(ctx, s); return st; }
+  if (large && ctx->opt_upload == 1)
+    upload_note_rate(ctx, packed, nbytes, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   *out = s;
   return LM_OK;
 }

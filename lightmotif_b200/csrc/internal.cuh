@@ -84,10 +84,14 @@ struct lm_ctx {
   size_t h_pin_bytes = 0;
   // large striped DNA matrices from host memory (lm_seq_from_striped): two-ended upload, upload.cu
   lm_uploader* uploader = nullptr;
-  int opt_upload = 1;                             // LM_OPT_UPLOAD: 0 plain copy, 1 plain + packed chunks, 2 packed chunks only
+  int opt_upload = 1;                             // LM_OPT_UPLOAD: 0 plain copy, 1 adaptive, 2 packed chunks only, 3 / 4 two-ended (gaps only / always)
   int opt_upload_threads = 0;                     // LM_OPT_UPLOAD_THREADS: host threads that pack (0 = all but one)
   long long opt_upload_min_bytes = 64ll << 20;    // LM_OPT_UPLOAD_MIN_BYTES: smaller matrices take the plain copy
   uint64_t upload_stats[4] = {0, 0, 0, 0};        // last upload: bytes over PCIe, packed chunks, plain chunks, threads
+  // LM_OPT_UPLOAD = 1: bytes/s the two-ended upload and the plain copy achieved on this context's last large
+  // uploads (0 = not tried yet); the faster one is used, the other re-tried every 32nd upload
+  double upload_rate_packed = 0.0, upload_rate_plain = 0.0;
+  uint32_t upload_calls = 0;
 };
 
 struct lm_seq {
@@ -150,7 +154,8 @@ int threshold_launch(lm_ctx* ctx, const lm_seq* seq, const float* pssm, size_t m
                      size_t row_end, float t, lm_hit* d_hits, size_t cap, size_t small_off, const lm::PeerLink* link,
                      lm::PrunePlan* plan_out);
 // upload.cu
-bool upload_wants_packed(const lm_ctx* ctx, int alphabet, size_t stride, size_t bytes);
+bool upload_wants_packed(lm_ctx* ctx, int alphabet, size_t stride, size_t bytes, const void* src);
+void upload_note_rate(lm_ctx* ctx, bool packed, size_t bytes, double seconds);
 int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t bytes);
 int check_score_args(size_t m, size_t rows, size_t wrap, size_t length, size_t row_begin, size_t row_end);
 

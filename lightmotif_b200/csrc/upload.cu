@@ -140,8 +140,27 @@ int get_uploader(lm_ctx* ctx, int threads, lm_uploader** out) {
 
 }  // namespace
 
-bool upload_wants_packed(const lm_ctx* ctx, int alphabet, size_t stride, size_t bytes) {
-  return ctx->opt_upload != 0 && alphabet == LM_DNA && stride == 32 && bytes >= (size_t)ctx->opt_upload_min_bytes;
+// Does this upload take the two-ended path?  LM_OPT_UPLOAD = 1 (default) decides from what this context has
+// measured: on a host whose memory system the copy engines of several ranks already saturate (4 ranks x 53 GB/s
+// on a 32-thread host), packing threads only take bandwidth away from them (measured: 175 vs 212 Gbp/s), while
+// one or two ranks per host gain 1.3-2.4x.  The first large upload goes two-ended, the second plain, later
+// ones take the faster of the two; the other is tried again every 32nd upload.  Pageable sources always pack.
+bool upload_wants_packed(lm_ctx* ctx, int alphabet, size_t stride, size_t bytes, const void* src) {
+  if (ctx->opt_upload == 0 || alphabet != LM_DNA || stride != 32 || bytes < (size_t)ctx->opt_upload_min_bytes) return false;
+  if (ctx->opt_upload != 1) return true;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) return true;
+  const uint32_t call = ctx->upload_calls++;
+  if (ctx->upload_rate_packed == 0.0) return true;
+  if (ctx->upload_rate_plain == 0.0) return false;
+  const bool packed_is_faster = ctx->upload_rate_packed >= ctx->upload_rate_plain;
+  return (call % 32 == 31) ? !packed_is_faster : packed_is_faster;
+}
+void upload_note_rate(lm_ctx* ctx, bool packed, size_t bytes, double seconds) {
+  if (seconds <= 0.0) return;
+  (packed ? ctx->upload_rate_packed : ctx->upload_rate_plain) = (double)bytes / seconds;
 }
 
 // Copy `bytes` DNA symbols (a striped matrix, or the flat symbols of lm_seq_from_symbols) from host memory to
@@ -161,7 +180,7 @@ int upload_striped_dna(lm_ctx* ctx, uint8_t* dst, const uint8_t* src, size_t byt
   const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
                       attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  const bool raw_front = pinned && ctx->opt_upload != 2;  // 2 = packed chunks only (tests, pageable sources)
+  const bool raw_front = pinned && ctx->opt_upload != 2;  // 2 = packed chunks only
   const bool raw_gaps_only = ctx->opt_upload == 3;       // 3 = plain chunks only while no packed copy is pending
   const int64_t nchunks = (int64_t)((bytes + CHUNK - 1) / CHUNK);
   auto chunk_len = [&](int64_t c) { return (size_t)c * CHUNK + CHUNK <= bytes ? CHUNK : bytes - (size_t)c * CHUNK; };

@@ -98,7 +98,7 @@ comm.close()
 # the exact kernel's prefix-table path (tiles without N)
 a = np.random.default_rng(3).integers(0, 4, size=((9 << 20) // 32 + 19, 32), dtype=np.uint8)
 a[5, 5] = 4
-for mode in (1, 2):
+for mode in (4, 2):
     dna.set_upload(mode, threads=2, min_bytes=0)
     up = dna.sequence_from_striped(a, (a.shape[0] - 19) * 32, 19)
     assert np.array_equal(up.download(), a)

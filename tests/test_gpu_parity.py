@@ -478,7 +478,7 @@ def _random_striped(rng, rows, wrap, n_frac=0.0):
     return a
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [4, 2])
 @pytest.mark.parametrize("pinned", [True, False])
 def test_packed_upload_is_byte_identical(lm, dna, mode, pinned):
     """lm_seq_from_striped of a large DNA matrix (plain chunks from the front, 2-bit packed chunks from the
@@ -520,7 +520,7 @@ def test_packed_upload_scan_equals_plain(lm, dna, jaspar):
     a[rows:] = np.roll(a[:wrap], -1, axis=1)          # wrap rows as configure_wrap leaves them (seq.rs:384-400)
     a[rows:, 31] = 4
     res = []
-    for mode in (0, 1, 2):
+    for mode in (0, 4, 2, 3):
         dna.set_upload(mode, threads=2, min_bytes=0)
         try:
             seq = dna.sequence_from_striped(a, rows * 32, wrap)
@@ -528,7 +528,7 @@ def test_packed_upload_scan_equals_plain(lm, dna, jaspar):
             seq.free()
         finally:
             dna.set_upload(1, 0, 64 << 20)
-    assert res[0] == res[1] == res[2]
+    assert res[0] == res[1] == res[2] == res[3]
     assert res[0][0] is not None
 
 
@@ -541,7 +541,7 @@ def test_packed_upload_of_flat_symbols(lm, dna):
     sym[5_000_000:5_000_300] = 4
     sym[-1] = 4
     want = O.stripe(O.DNA, sym, 32, 9)
-    for mode in (0, 1, 2):
+    for mode in (0, 4, 2):
         dna.set_upload(mode, threads=3, min_bytes=0)
         try:
             seq = dna.sequence_from_symbols(sym, 9)
@@ -553,3 +553,25 @@ def test_packed_upload_of_flat_symbols(lm, dna):
         assert np.array_equal(got, want), mode
         if mode:
             assert up["packed_chunks"] >= 1 and up["pcie_bytes"] < n
+
+
+def test_adaptive_upload_measures_both_ways_then_keeps_one(lm, dna):
+    """LM_OPT_UPLOAD = 1: the first large upload is two-ended, the second plain, later ones whichever was
+    faster -- and the device matrix is the caller's bytes every time."""
+    import torch
+    rng = np.random.default_rng(31)
+    rows, wrap = (24 << 20) // 32, 19
+    a = _random_striped(rng, rows, wrap)
+    host = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = a
+    dna.set_upload(1, threads=3, min_bytes=0)
+    ways = []
+    try:
+        for _ in range(4):
+            seq = dna.sequence_from_striped(host.numpy(), rows * 32, wrap)
+            ways.append(dna.last_upload["threads"] > 0)
+            assert np.array_equal(seq.download(), a)
+            seq.free()
+    finally:
+        dna.set_upload(1, 0, 64 << 20)
+    assert ways[0] is True and ways[1] is False and ways[2] == ways[3]

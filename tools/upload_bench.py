@@ -34,7 +34,7 @@ def main():
     pli = lm.Pipeline.cuda(lm.DNA)
     print(f"# {cores} host threads available, matrix {h.nbytes / 1e9:.2f} GB pinned")
     ts = [int(t) for t in (a.threads.split(",") if a.threads else [str(max(1, cores - 1))])]
-    combos = [(0, 0)] + [(m, t) for m in (1, 3, 2) for t in ts]
+    combos = [(0, 0)] + [(m, t) for m in (4, 3, 2, 1) for t in ts]
     for mode, thr in combos:
         pli.set_upload(mode, thr)
         ts = []
