@@ -585,10 +585,10 @@ def run_ours(args):
 
         def e2e_run(mode, threads):
             pli.set_upload(mode, threads)
-            for _ in range(2):  # (mode 1 times its first upload two-ended and its second plain, then keeps the faster)
+            for _ in range(3):  # (mode 1: the first upload allocates the pinned ring, the second is timed two-ended, the third plain)
                 e2e_step()
             sync_all()
-            n = max(3, min(args.steps, 5))
+            n = max(3, min(args.steps, 10))
             t0 = time.perf_counter()
             for _ in range(n):
                 r = e2e_step()

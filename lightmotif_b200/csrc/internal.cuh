@@ -92,6 +92,7 @@ struct lm_ctx {
   // uploads (0 = not tried yet); the faster one is used, the other re-tried every 32nd upload
   double upload_rate_packed = 0.0, upload_rate_plain = 0.0;
   uint32_t upload_calls = 0;
+  bool upload_ring_created = false;               // the last two-ended upload also allocated the ring: its time is not a rate
 };
 
 struct lm_seq {

@@ -115,7 +115,9 @@ int upload_threads(const lm_ctx* ctx) {
 
 int get_uploader(lm_ctx* ctx, int threads, lm_uploader** out) {
   const int want = 2 * threads + 8;  // (a packed chunk may wait behind plain ones: spare slots keep the packers busy)
+  ctx->upload_ring_created = false;
   if (ctx->uploader && ctx->uploader->nslots >= want) { *out = ctx->uploader; return LM_OK; }
+  ctx->upload_ring_created = true;
   free_uploader(ctx->uploader);
   ctx->uploader = nullptr;
   lm_uploader* u = new (std::nothrow) lm_uploader();
@@ -160,6 +162,7 @@ bool upload_wants_packed(lm_ctx* ctx, int alphabet, size_t stride, size_t bytes,
 }
 void upload_note_rate(lm_ctx* ctx, bool packed, size_t bytes, double seconds) {
   if (seconds <= 0.0) return;
+  if (packed && ctx->upload_ring_created) return;  // (pinned allocations took part of that time: measure the next one)
   (packed ? ctx->upload_rate_packed : ctx->upload_rate_plain) = (double)bytes / seconds;
 }
 

@@ -567,6 +567,9 @@ def test_adaptive_upload_measures_both_ways_then_keeps_one(lm, dna):
     dna.set_upload(1, threads=3, min_bytes=0)
     ways = []
     try:
+        dna.set_upload(4, threads=3, min_bytes=0)          # (the ring exists before the measurements start)
+        dna.sequence_from_striped(host.numpy(), rows * 32, wrap).free()
+        dna.set_upload(1, threads=3, min_bytes=0)
         for _ in range(4):
             seq = dna.sequence_from_striped(host.numpy(), rows * 32, wrap)
             ways.append(dna.last_upload["threads"] > 0)
