@@ -157,7 +157,8 @@ bool upload_wants_packed(lm_ctx* ctx, int alphabet, size_t stride, size_t bytes,
   const uint32_t call = ctx->upload_calls++;
   if (ctx->upload_rate_packed == 0.0) return true;
   if (ctx->upload_rate_plain == 0.0) return false;
-  const bool packed_is_faster = ctx->upload_rate_packed >= ctx->upload_rate_plain;
+  // (a tie goes to the plain copy: it costs no host threads)
+  const bool packed_is_faster = ctx->upload_rate_packed >= 1.05 * ctx->upload_rate_plain;
   return (call % 32 == 31) ? !packed_is_faster : packed_is_faster;
 }
 void upload_note_rate(lm_ctx* ctx, bool packed, size_t bytes, double seconds) {
