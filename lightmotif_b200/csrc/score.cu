@@ -90,6 +90,12 @@ __host__ __device__ inline SmemLayout smem_layout(int kp, int m_pad, bool prefix
   L.total = L.table4_off + (prefix ? TABLE4_BYTES : 0);
   return L;
 }
+constexpr uint32_t SMEM_LIMIT = 200 * 1024;
+// the prefix table is used when the launch is DNA f32 with one motif AND it still fits (very long motifs:
+// their tables take the room)
+__host__ __device__ inline bool wants_prefix(int kp, bool u8, int n_motifs, int m_pad) {
+  return kp == 16 && !u8 && n_motifs == 1 && smem_layout(kp, m_pad, true).total <= SMEM_LIMIT;
+}
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
   return __byte_perm(a, b, s);
@@ -150,7 +156,7 @@ template <int KP, int MODE, bool U8>
 __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(const ScoreArgs a, uint64_t num_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool PAIRS = KP == 16 && !U8;  // the paired-position path exists for DNA f32
-  const bool prefix = PAIRS && a.n_motifs == 1;
+  const bool prefix = wants_prefix(KP, U8, a.n_motifs, a.m_pad);
   const SmemLayout L = smem_layout(KP, a.m_pad, prefix);
   uint32_t* table = reinterpret_cast<uint32_t*>(smem);
   uint32_t* tilet = reinterpret_cast<uint32_t*>(smem + L.tilet_off);
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
             // prefix table: entry (s0, s1, s2, s3) = ((( +0.0 + w0[s0]) + w1[s1]) + w2[s2]) + w3[s3], the exact value
             // every position's accumulator has after its first four motif rows (rows >= m are +0.0), replicated
             // once per lane so that a warp reads 32 different entries in one bank pass
-            for (int idx = tid; idx < 256 * 32; idx += THREADS) {
+            for (int idx = tid; prefix && idx < 256 * 32; idx += THREADS) {
               const int e = idx >> 5;
               float v = __fadd_rn(0.0f, tf[0 * KP + (e & 3)]);
               v = __fadd_rn(v, tf[1 * KP + ((e >> 2) & 3)]);
@@ -294,7 +300,8 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
         // look-ups.  The sequential sum starts at +0.0, so its first four steps depend on four symbols only and
         // can be tabulated exactly; later steps depend on the running value and cannot.  The index comes from the
         // window bytes (4 s each): dp4a with (1, 4, 16, 64) = 4 * (s0 + 4 s1 + 16 s2 + 64 s3).
-        {
+        int j4 = 0;
+        if (prefix) {
           W[NWIN - 1] = colp[NWIN - 1];
           const uint32_t t4 = smem_u32(table4) + lane * 4;
           float v[RPT];
@@ -310,10 +317,11 @@ __global__ void __launch_bounds__(THREADS, LM_SCORE_MINBLOCKS) score_kernel(cons
 #pragma unroll
           for (int k = 0; k < NWIN - 1; ++k) W[k] = W[k + 1];
           gbase2 += 4 * 128;
+          j4 = 1;
         }
 #pragma unroll
         for (int k = 0; k < NWIN - 2; ++k) P[k] = pair_codes(W[k], W[k + 1]);
-        for (int j4 = 1; j4 < m_pad / 4; ++j4) {
+        for (; j4 < m_pad / 4; ++j4) {
           W[NWIN - 1] = colp[j4 + NWIN - 1];
           P[NWIN - 2] = pair_codes(W[NWIN - 2], W[NWIN - 1]);
           P[NWIN - 1] = pair_codes(W[NWIN - 1], 0u);  // only its first two codes (bytes 16, 17) are used
@@ -441,8 +449,8 @@ cudaError_t launch_mode(int mode, const ScoreArgs& a, int sm_count, cudaStream_t
   const uint64_t n_rows = a.row_end - a.row_begin;
   const uint64_t num_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
   if (num_tiles == 0) return cudaSuccess;
-  const SmemLayout L = smem_layout(KP, a.m_pad, KP == 16 && !U8 && a.n_motifs == 1);
-  if (L.total > 200 * 1024) return cudaErrorInvalidValue;
+  const SmemLayout L = smem_layout(KP, a.m_pad, wants_prefix(KP, U8, a.n_motifs, a.m_pad));
+  if (L.total > SMEM_LIMIT) return cudaErrorInvalidValue;
   void (*kern)(const ScoreArgs, uint64_t) = nullptr;
   switch (mode) {
 #define LM_CASE(M) case M: kern = score_kernel<KP, M, U8>; break;

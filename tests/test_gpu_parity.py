@@ -578,3 +578,18 @@ def test_adaptive_upload_measures_both_ways_then_keeps_one(lm, dna):
     finally:
         dna.set_upload(1, 0, 64 << 20)
     assert ways[0] is True and ways[1] is False and ways[2] == ways[3]
+
+
+@pytest.mark.parametrize("m", [500, 560])
+def test_score_very_long_motifs(dna, m):
+    """Motifs so long that their tables crowd the exact kernel's shared memory: at m = 500 the 4-row prefix
+    table still fits, at m = 560 the kernel must do without it -- bit-identical scores either way."""
+    rng = np.random.default_rng(m)
+    pssm = random_pssm(rng, m, 5)
+    n = 60_013
+    sym = rng.integers(0, 4, n).astype(np.uint8)   # no N: the paired-position path
+    seq = dna.sequence_from_symbols(sym, m - 1)
+    got = seq.score(pssm)
+    want = O.score_f32(pssm, O.stripe(O.DNA, sym, 32, m - 1), n)
+    assert np.array_equal(bits(got), bits(want))
+    seq.free()
