@@ -20,12 +20,25 @@ def main():
     ap.add_argument("--gb", type=float, default=5.0)
     ap.add_argument("--threads", default="")
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--thp", action="store_true", help="host matrix in transparent huge pages, pinned with cudaHostRegister")
     a = ap.parse_args()
     cores = len(os.sched_getaffinity(0))
     rows = int(a.gb * 1e9) // 32
     wrap = 19
-    host = torch.empty((rows + wrap, 32), dtype=torch.uint8, pin_memory=True)
-    h = host.numpy()
+    if a.thp:
+        import mmap
+        nbytes = (rows + wrap) * 32
+        size = -(-nbytes // (2 << 20)) * (2 << 20)
+        mm = mmap.mmap(-1, size, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        mm.madvise(mmap.MADV_HUGEPAGE)
+        h = np.frombuffer(mm, dtype=np.uint8, count=nbytes).reshape(rows + wrap, 32)
+        h[:] = 0  # fault the pages in (as huge pages where the kernel grants them)
+        rc = torch.cuda.cudart().cudaHostRegister(h.ctypes.data, size, 0)
+        print("# cudaHostRegister ->", rc, " AnonHugePages:", [l for l in open("/proc/meminfo") if "AnonHugePages" in l][0].strip(),
+              " thp:", open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip())
+    else:
+        host = torch.empty((rows + wrap, 32), dtype=torch.uint8, pin_memory=True)
+        h = host.numpy()
     rng = np.random.default_rng(1)
     blk = rng.integers(0, 4, size=(1 << 20, 32), dtype=np.uint8)
     for r0 in range(0, rows + wrap, 1 << 20):
